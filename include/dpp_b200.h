@@ -1,0 +1,179 @@
+/*
+ * dpp_b200.h -- C ABI of libdppb200.so: the B200 (sm_100a) implementation of perphil's hot path,
+ * "assemble + solve the linear double-porosity/permeability (DPP) pressure system".
+ *
+ * perphil (reference, /root/reference) has no FFI of its own: its hot path is
+ *     perphil.solvers.solver.solve_dpp            (src/perphil/solvers/solver.py:30-76)
+ *     perphil.forms.dpp.dpp_form                  (src/perphil/forms/dpp.py:95-132)
+ *     perphil.solvers.conditioning.get_matrix_data_from_form   (src/perphil/solvers/conditioning.py:66-102)
+ * and everything below those calls runs inside Firedrake/PETSc.  The entry points declared here
+ * are what a ctypes binding for that path binds instead; each one names the
+ * reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative dpp_status; dpp_last_error() gives text;
+ *   - plain pointers and sizes only; the caller owns every HOST buffer it passes, the library
+ *     copies what it needs to the device and owns all device memory until dpp_destroy();
+ *   - pointers named *_host are host memory; pointers named *_dev are device memory of the
+ *     handle's GPU; calls are blocking unless stated; one handle = one GPU = one CUDA stream;
+ *   - DOF layout everywhere: field-blocked [p1(0..n_nodes-1) ; p2(0..n_nodes-1)], node numbering
+ *     exactly as supplied in cell_node_map (iterative_bench.py:323-324 relies on this layout);
+ *   - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef DPP_B200_H
+#define DPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dpp_context* dpp_handle;
+
+typedef enum {
+  DPP_OK = 0,
+  DPP_ERR_INVALID = -1,     /* bad argument / unsupported combination           */
+  DPP_ERR_CUDA = -2,        /* CUDA runtime error                               */
+  DPP_ERR_STATE = -3,       /* call order (e.g. solve before set_params)        */
+  DPP_ERR_NCCL = -4,        /* NCCL error                                       */
+  DPP_ERR_NO_DEVICE = -5    /* no usable sm_100 GPU: the library never falls back */
+} dpp_status;
+
+/* KSP / PC vocabulary mirrors the PETSc option values used in solvers/parameters.py:1-57 */
+typedef enum { DPP_KSP_CG = 0, DPP_KSP_GMRES = 1, DPP_KSP_PICARD = 2 } dpp_ksp_type;
+typedef enum { DPP_PC_NONE = 0, DPP_PC_JACOBI = 1, DPP_PC_PBJACOBI = 2, DPP_PC_FIELDSPLIT = 3 } dpp_pc_type;
+typedef enum { DPP_FS_ADDITIVE = 0, DPP_FS_MULTIPLICATIVE = 1 } dpp_fieldsplit_type;
+typedef enum { DPP_INNER_PREONLY = 0, DPP_INNER_CG = 1 } dpp_inner_ksp_type;
+typedef enum { DPP_OP_MATRIX_FREE = 0, DPP_OP_ASSEMBLED = 1 } dpp_operator_mode;
+/* which matrix-free kernel family serves the handle (reported by dpp_get_info) */
+typedef enum { DPP_KERNEL_GENERAL = 0, DPP_KERNEL_STRUCTURED = 1 } dpp_kernel_family;
+
+/* PETSc KSPConvergedReason values (positive = converged) */
+enum {
+  DPP_CONVERGED_RTOL = 2, DPP_CONVERGED_ATOL = 3, DPP_CONVERGED_ITS = 4,
+  DPP_DIVERGED_ITS = -3, DPP_DIVERGED_DTOL = -4, DPP_DIVERGED_BREAKDOWN = -5,
+  DPP_DIVERGED_INDEFINITE_MAT = -10, DPP_DIVERGED_NANORINF = -9
+};
+
+typedef struct {
+  int32_t ksp_type;          /* dpp_ksp_type         <- "ksp_type" / "snes_type" (Picard)         */
+  int32_t pc_type;           /* dpp_pc_type          <- "pc_type"                                 */
+  int32_t fieldsplit_type;   /* dpp_fieldsplit_type  <- "pc_fieldsplit_type"                      */
+  int32_t inner_ksp_type;    /* dpp_inner_ksp_type   <- "fieldsplit_{0,1}" -> "ksp_type"          */
+  int32_t inner_pc_type;     /* NONE | JACOBI        <- "fieldsplit_{0,1}" -> "pc_type"           */
+  int32_t operator_mode;     /* dpp_operator_mode    <- "mat_type": "matfree" | "aij"             */
+  int32_t max_it;            /* "ksp_max_it" (50000 in solvers/parameters.py:1)                   */
+  int32_t gmres_restart;     /* "ksp_gmres_restart" (PETSc default 30)                            */
+  int32_t inner_max_it;
+  int32_t check_every;       /* host polls the device convergence flag every N iterations (>=1)   */
+  double rtol;               /* "ksp_rtol" 1e-8 (parameters.py:14)                                */
+  double atol;               /* "ksp_atol" 1e-12                                                  */
+  double dtol;               /* PETSc default 1e4                                                 */
+  double inner_rtol;
+  double inner_atol;
+} dpp_options;
+
+typedef struct {
+  int32_t iterations;        /* KSP its (outer)        -> Solution.iteration_number (solver.py:73) */
+  int32_t converged_reason;  /* KSPConvergedReason                                                 */
+  int32_t inner_iterations;  /* total inner (fieldsplit / Picard block) CG iterations              */
+  int32_t history_len;       /* entries written to residual_history                                */
+  double residual_norm;      /* KSP residual norm      -> Solution.residual_error (solver.py:74)   */
+  double rhs_norm;           /* ||b||_2 of the lifted system = "0 SNES Function norm"              */
+  double solve_ms;           /* device time of the Krylov loop (CUDA events)                       */
+  double setup_ms;           /* device time of lifting + preconditioner setup                      */
+  double apply_ms;           /* device time spent in operator applies inside the solve             */
+  int64_t apply_count;
+} dpp_result;
+
+typedef struct {
+  int32_t kernel_family;     /* dpp_kernel_family */
+  int32_t dim, degree;
+  int32_t grid_nodes[3];     /* structured: nodes per axis (x slowest); else 0 */
+  int64_t n_nodes, n_cells, n_owned_nodes;
+  int32_t rank, world;
+  int32_t sm_count;
+  int64_t device_bytes;      /* device memory held by the handle */
+} dpp_info;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* Upload one mesh + scalar function space V (W = V x V).  Replaces what Firedrake derives from
+ * MixedFunctionSpace((V, V)) in solver.py:64-69: V.cell_node_map().values, mesh.coordinates.
+ *   cell_node_map        [n_cells * nodes_per_cell] int32, local order tensor-lexicographic
+ *                        (x slowest); nodes_per_cell = (degree+1)^dim
+ *   coords               [n_coord_nodes * dim] vertex coordinates (the Q1 coordinate field)
+ *   coord_cell_node_map  [n_cells * 2^dim] (may alias cell_node_map when degree == 1)
+ * The library inspects the data: a rectilinear tensor grid numbered lexicographically selects the
+ * DPP_KERNEL_STRUCTURED family, anything else DPP_KERNEL_GENERAL. */
+int dpp_create(dpp_handle* h, int device, int dim, int degree, int64_t n_nodes, int64_t n_cells,
+               int nodes_per_cell, const int32_t* cell_node_map_host, int64_t n_coord_nodes,
+               const double* coords_host, const int32_t* coord_cell_node_map_host);
+void dpp_destroy(dpp_handle h);
+const char* dpp_last_error(dpp_handle h); /* h may be NULL: error of the last failed dpp_create */
+int dpp_get_info(dpp_handle h, dpp_info* info);
+/* force a kernel family (testing: run the general kernels on a structured mesh). Call before
+ * set_params/set_dirichlet. */
+int dpp_force_kernel_family(dpp_handle h, int family);
+
+/* DPPParameters (models/dpp/parameters.py:5-53): float(k1), float(k2), float(beta), float(mu). */
+int dpp_set_params(dpp_handle h, double k1, double k2, double beta, double mu);
+
+/* fd.DirichletBC(W.sub(field), g, ...) (README.md:79-82): bc.nodes and g at those nodes.
+ * Replaces the previous set for that field; n == 0 clears it. */
+int dpp_set_dirichlet(dpp_handle h, int field, int64_t n, const int32_t* nodes_host, const double* values_host);
+
+/* ---- distributed (slab partition; one handle per rank/GPU) ---------------------------------- */
+
+/* The local mesh holds owned + ghost nodes; rows are computed for local ids [owned_begin,
+ * owned_end).  nccl_unique_id = the 128-byte ncclUniqueId created by rank 0 and broadcast by the
+ * host layer (torch.distributed). */
+int dpp_comm_init(dpp_handle h, int rank, int world, const void* nccl_unique_id, int64_t owned_begin,
+                  int64_t owned_end);
+/* ncclGetUniqueId into a caller-provided 128-byte buffer (rank 0 calls it, the host layer broadcasts) */
+int dpp_nccl_unique_id(void* out128);
+/* one neighbour: local node ids whose values are sent to / received from `peer` before an apply */
+int dpp_comm_add_neighbor(dpp_handle h, int peer, int64_t n_send, const int32_t* send_nodes_host,
+                          int64_t n_recv, const int32_t* recv_nodes_host);
+
+/* ---- operator ------------------------------------------------------------------------------- */
+
+/* y = A_bc x with A_bc = P A P + (I - P) (Firedrake DirichletBC semantics), A the dpp_form matrix
+ * (forms/dpp.py:27,57,89).  x, y: [2*n_nodes] doubles.  This is PETSc MatMult on the path
+ * (solver.py:71).  *_dev variant: no copies, asynchronous on the handle's stream. */
+int dpp_apply_host(dpp_handle h, const double* x_host, double* y_host, int operator_mode);
+int dpp_apply_dev(dpp_handle h, const double* x_dev, double* y_dev, int operator_mode);
+/* diag(A_bc) -> [2*n_nodes] */
+int dpp_get_diagonal_host(dpp_handle h, double* diag_host);
+
+/* ---- assembly: fd.assemble(a, bcs=bcs, mat_type="aij") (conditioning.py:51-63) --------------- */
+
+/* Builds the 2x2-block CSR (full element pattern, sorted columns, explicit zeros where Dirichlet
+ * rows/columns were eliminated -- conditioning.py:86 then calls eliminate_zeros()). */
+int dpp_assemble_csr(dpp_handle h, int64_t* nnz);
+/* petsc_matrix.getValuesCSR() (conditioning.py:85): indptr [2*n_nodes+1], indices/data [nnz] */
+int dpp_get_csr_host(dpp_handle h, int64_t* indptr_host, int32_t* indices_host, double* data_host);
+
+/* ---- solve: LinearVariationalSolver.solve() + ksp getters (solver.py:66-74) ------------------ */
+
+void dpp_default_options(dpp_options* opt);
+/* Lifts the Dirichlet data (u0 = g on Gamma; b = -(A u0) on interior rows), solves A_bc d = b
+ * from d = 0 with the configured Krylov method, writes u = u0 + d.  u_host: [2*n_nodes] (may be
+ * NULL: keep the solution on the device, see dpp_solution_dev).  residual_history (optional):
+ * one entry per KSP iteration starting with iteration 0, like -ksp_monitor. */
+int dpp_solve(dpp_handle h, const dpp_options* opt, double* u_host, dpp_result* result,
+              double* residual_history_host, int32_t history_capacity);
+const double* dpp_solution_dev(dpp_handle h);
+
+/* ---- measurement helpers (bench.py; timed with CUDA events on the handle's stream) ----------- */
+
+/* mean device milliseconds of `reps` back-to-back applies of the monolithic operator on internal
+ * vectors (after `warmup` untimed ones); with_dot fuses the (x, Ax) reduction as CG uses it. */
+int dpp_time_apply(dpp_handle h, int operator_mode, int warmup, int reps, int with_dot, double* mean_ms);
+int dpp_kernel_launch_count(dpp_handle h, int64_t* launches); /* kernels launched so far by this handle */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPP_B200_H */

@@ -1,0 +1,163 @@
+"""numpy-facing wrapper of one libdppb200 handle (one mesh + function space on one GPU)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+class DppError(RuntimeError):
+    pass
+
+
+@dataclass
+class SolveInfo:
+    iterations: int
+    converged_reason: int
+    inner_iterations: int
+    residual_norm: float
+    rhs_norm: float
+    solve_ms: float
+    setup_ms: float
+    apply_count: int
+    history: np.ndarray
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DppHandle:
+    """Owns the device copy of a mesh/function space; mirrors include/dpp_b200.h one to one."""
+
+    def __init__(self, dim: int, degree: int, cell_node_map: np.ndarray, coords: np.ndarray,
+                 coord_cell_node_map: Optional[np.ndarray] = None, n_nodes: Optional[int] = None, device: int = 0):
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        cnm = np.ascontiguousarray(cell_node_map, dtype=np.int32)
+        xyz = np.ascontiguousarray(coords, dtype=np.float64)
+        ccnm = cnm if coord_cell_node_map is None else np.ascontiguousarray(coord_cell_node_map, dtype=np.int32)
+        if n_nodes is None:
+            n_nodes = int(cnm.max()) + 1
+        self.n_nodes = int(n_nodes)
+        self.dim, self.degree = dim, degree
+        rc = self._lib.dpp_create(C.byref(self._h), device, dim, degree, self.n_nodes, cnm.shape[0], cnm.shape[1],
+                                  _ptr(cnm), xyz.shape[0], _ptr(xyz), _ptr(ccnm))
+        if rc != 0:
+            msg = self._lib.dpp_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise DppError(f"dpp_create failed ({rc}): {msg}")
+
+    # -- plumbing
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise DppError(f"{what} failed ({rc}): {self._lib.dpp_last_error(self._h).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.dpp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setup
+    def info(self) -> L.DppInfo:
+        info = L.DppInfo()
+        self._check(self._lib.dpp_get_info(self._h, C.byref(info)), "dpp_get_info")
+        return info
+
+    def force_kernel_family(self, family: int):
+        self._check(self._lib.dpp_force_kernel_family(self._h, family), "dpp_force_kernel_family")
+
+    def set_params(self, k1: float, k2: float, beta: float, mu: float):
+        self._check(self._lib.dpp_set_params(self._h, float(k1), float(k2), float(beta), float(mu)), "dpp_set_params")
+
+    def set_dirichlet(self, field: int, nodes: Sequence[int], values: Sequence[float]):
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if nodes.shape != values.shape:
+            raise ValueError("nodes and values must have the same length")
+        self._check(self._lib.dpp_set_dirichlet(self._h, field, nodes.size, _ptr(nodes), _ptr(values)),
+                    "dpp_set_dirichlet")
+
+    def comm_init(self, rank: int, world: int, unique_id: Optional[bytes], owned_begin: int, owned_end: int):
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._check(self._lib.dpp_comm_init(self._h, rank, world, buf, owned_begin, owned_end), "dpp_comm_init")
+
+    def comm_add_neighbor(self, peer: int, send_nodes, recv_nodes):
+        s = np.ascontiguousarray(send_nodes, dtype=np.int32)
+        r = np.ascontiguousarray(recv_nodes, dtype=np.int32)
+        self._check(self._lib.dpp_comm_add_neighbor(self._h, peer, s.size, _ptr(s), r.size, _ptr(r)),
+                    "dpp_comm_add_neighbor")
+
+    # -- operator
+    def apply(self, x: np.ndarray, assembled: bool = False) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.size != 2 * self.n_nodes:
+            raise ValueError("x must have 2*n_nodes entries")
+        y = np.empty_like(x)
+        self._check(self._lib.dpp_apply_host(self._h, _ptr(x), _ptr(y), L.OP_ASSEMBLED if assembled else L.OP_MATRIX_FREE),
+                    "dpp_apply_host")
+        return y
+
+    def diagonal(self) -> np.ndarray:
+        d = np.empty(2 * self.n_nodes)
+        self._check(self._lib.dpp_get_diagonal_host(self._h, _ptr(d)), "dpp_get_diagonal_host")
+        return d
+
+    def assemble_csr(self):
+        nnz = C.c_int64()
+        self._check(self._lib.dpp_assemble_csr(self._h, C.byref(nnz)), "dpp_assemble_csr")
+        indptr = np.empty(2 * self.n_nodes + 1, dtype=np.int64)
+        indices = np.empty(nnz.value, dtype=np.int32)
+        data = np.empty(nnz.value, dtype=np.float64)
+        self._check(self._lib.dpp_get_csr_host(self._h, _ptr(indptr), _ptr(indices), _ptr(data)), "dpp_get_csr_host")
+        return indptr, indices, data
+
+    # -- solve
+    def default_options(self) -> L.DppOptions:
+        o = L.DppOptions()
+        self._lib.dpp_default_options(C.byref(o))
+        return o
+
+    def solve(self, options: Optional[L.DppOptions] = None, want_solution: bool = True, history: int = 0,
+              out: Optional[np.ndarray] = None):
+        opt = options if options is not None else self.default_options()
+        u = None
+        if want_solution:
+            u = out if out is not None else np.empty(2 * self.n_nodes)
+        hist = np.zeros(max(history, 0))
+        res = L.DppResult()
+        self._check(self._lib.dpp_solve(self._h, C.byref(opt), _ptr(u), C.byref(res), _ptr(hist) if history > 0 else None,
+                                        int(history)), "dpp_solve")
+        info = SolveInfo(res.iterations, res.converged_reason, res.inner_iterations, res.residual_norm, res.rhs_norm,
+                         res.solve_ms, res.setup_ms, res.apply_count, hist[: res.history_len].copy())
+        return u, info
+
+    # -- measurement
+    def time_apply(self, reps: int = 20, warmup: int = 3, assembled: bool = False, with_dot: bool = False) -> float:
+        ms = C.c_double()
+        self._check(self._lib.dpp_time_apply(self._h, L.OP_ASSEMBLED if assembled else L.OP_MATRIX_FREE, warmup, reps,
+                                             1 if with_dot else 0, C.byref(ms)), "dpp_time_apply")
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._check(self._lib.dpp_kernel_launch_count(self._h, C.byref(n)), "dpp_kernel_launch_count")
+        return n.value
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = L.load().dpp_nccl_unique_id(buf)
+    if rc != 0:
+        raise DppError(f"dpp_nccl_unique_id failed ({rc})")
+    return buf.raw

@@ -1,0 +1,240 @@
+// Slab-partition communication: NCCL over NVLink 5 / NVSwitch.
+//   - halo exchange before an apply: each rank sends the node planes its neighbours' boundary cells
+//     touch (grouped ncclSend/ncclRecv, <= 2 peers for slabs; SURVEY 8e "forward halo");
+//   - ncclAllReduce(sum, fp64) of the 1..31 Krylov scalars.
+// Replaces PETSc VecScatter + MPI_Allreduce of an mpiexec run of the reference.
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound at run time (see NcclApi)
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "dpp_internal.cuh"
+
+namespace dpp {
+
+// NCCL is resolved with dlopen on first use instead of a link-time dependency: a single-GPU
+// process never loads it, and a process that already holds PyTorch's bundled libnccl.so.2 reuses
+// that copy (RTLD_NOLOAD) instead of pulling a second, older one into the namespace.
+struct NcclApi {
+  void* so = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+  bool ok = false;
+};
+
+static NcclApi& nccl() {
+  static NcclApi api;
+  if (api.ok || !api.error.empty()) return api;
+  const char* env = getenv("DPP_NCCL_LIBRARY");
+  if (env && *env) api.so = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+  if (!api.so) api.so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!api.so) api.so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!api.so) {
+    api.error = std::string("cannot load libnccl.so.2: ") + dlerror();
+    return api;
+  }
+#define DPP_SYM(field, name)                                              \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.so, name)); \
+  if (!api.field) { api.error = std::string("libnccl.so.2 lacks ") + name; return api; }
+  DPP_SYM(GetUniqueId, "ncclGetUniqueId")
+  DPP_SYM(CommInitRank, "ncclCommInitRank")
+  DPP_SYM(CommDestroy, "ncclCommDestroy")
+  DPP_SYM(Send, "ncclSend")
+  DPP_SYM(Recv, "ncclRecv")
+  DPP_SYM(AllReduce, "ncclAllReduce")
+  DPP_SYM(GroupStart, "ncclGroupStart")
+  DPP_SYM(GroupEnd, "ncclGroupEnd")
+  DPP_SYM(GetErrorString, "ncclGetErrorString")
+#undef DPP_SYM
+  api.ok = true;
+  return api;
+}
+
+struct Neighbor {
+  int peer = -1;
+  int64_t n_send = 0, n_recv = 0;
+  int32_t *d_send_idx = nullptr, *d_recv_idx = nullptr;
+  double *d_sendbuf = nullptr, *d_recvbuf = nullptr;  // [2 * n]
+  bool send_contig = false, recv_contig = false;
+  int64_t send0 = 0, recv0 = 0;
+};
+
+struct Comm {
+  ncclComm_t comm = nullptr;
+  std::vector<Neighbor> nbrs;
+};
+
+namespace {
+
+#define DPP_NCCL(call)                                                                   \
+  do {                                                                                   \
+    ncclResult_t r__ = (call);                                                           \
+    if (r__ != ncclSuccess) {                                                            \
+      ctx->set_error(std::string(#call) + ": " + nccl().GetErrorString(r__));            \
+      return DPP_ERR_NCCL;                                                               \
+    }                                                                                    \
+  } while (0)
+
+__global__ void k_pack(long long n, const int32_t* __restrict__ idx, const double* __restrict__ f0,
+                       const double* __restrict__ f1, double* __restrict__ buf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = idx[i];
+    buf[i] = f0[s];
+    if (f1 != nullptr) buf[n + i] = f1[s];
+  }
+}
+
+__global__ void k_unpack(long long n, const int32_t* __restrict__ idx, double* __restrict__ f0, double* __restrict__ f1,
+                         const double* __restrict__ buf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = idx[i];
+    f0[s] = buf[i];
+    if (f1 != nullptr) f1[s] = buf[n + i];
+  }
+}
+
+bool contiguous(const int32_t* v, int64_t n) {
+  for (int64_t i = 1; i < n; ++i)
+    if (v[i] != v[0] + i) return false;
+  return n > 0;
+}
+
+}  // namespace
+
+int comm_halo_exchange(dpp_context* ctx, double* const* fields, int nf) {
+  Comm* C = ctx->comm;
+  if (!C || ctx->world <= 1) return DPP_OK;
+  for (Neighbor& nb : C->nbrs) {
+    if (nb.n_send > 0 && !nb.send_contig) {
+      const int blocks = (int)std::min<int64_t>((nb.n_send + 255) / 256, 1024);
+      k_pack<<<blocks, 256, 0, ctx->stream>>>(nb.n_send, nb.d_send_idx, fields[0], nf == 2 ? fields[1] : nullptr, nb.d_sendbuf);
+      ctx->launches++;
+    }
+  }
+  DPP_NCCL(nccl().GroupStart());
+  for (Neighbor& nb : C->nbrs) {
+    for (int f = 0; f < nf; ++f) {
+      if (nb.n_send > 0) {
+        const double* src = nb.send_contig ? fields[f] + nb.send0 : nb.d_sendbuf + f * nb.n_send;
+        DPP_NCCL(nccl().Send(src, (size_t)nb.n_send, ncclDouble, nb.peer, C->comm, ctx->stream));
+      }
+      if (nb.n_recv > 0) {
+        double* dst = nb.recv_contig ? fields[f] + nb.recv0 : nb.d_recvbuf + f * nb.n_recv;
+        DPP_NCCL(nccl().Recv(dst, (size_t)nb.n_recv, ncclDouble, nb.peer, C->comm, ctx->stream));
+      }
+    }
+  }
+  DPP_NCCL(nccl().GroupEnd());
+  for (Neighbor& nb : C->nbrs) {
+    if (nb.n_recv > 0 && !nb.recv_contig) {
+      const int blocks = (int)std::min<int64_t>((nb.n_recv + 255) / 256, 1024);
+      k_unpack<<<blocks, 256, 0, ctx->stream>>>(nb.n_recv, nb.d_recv_idx, fields[0], nf == 2 ? fields[1] : nullptr, nb.d_recvbuf);
+      ctx->launches++;
+    }
+  }
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+
+int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n) {
+  Comm* C = ctx->comm;
+  if (!C || ctx->world <= 1) return DPP_OK;
+  DPP_NCCL(nccl().AllReduce(d_vals, d_vals, (size_t)n, ncclDouble, ncclSum, C->comm, ctx->stream));
+  return DPP_OK;
+}
+
+void comm_destroy(dpp_context* ctx) {
+  Comm* C = ctx->comm;
+  if (!C) return;
+  for (Neighbor& nb : C->nbrs) {
+    void* p[] = {nb.d_send_idx, nb.d_recv_idx, nb.d_sendbuf, nb.d_recvbuf};
+    for (void* q : p)
+      if (q) cudaFree(q);
+  }
+  if (C->comm && nccl().ok) nccl().CommDestroy(C->comm);
+  delete C;
+  ctx->comm = nullptr;
+}
+
+}  // namespace dpp
+
+extern "C" {
+
+int dpp_nccl_unique_id(void* out128) {
+  if (!out128) return DPP_ERR_INVALID;
+  ncclUniqueId id;
+  if (!dpp::nccl().ok || dpp::nccl().GetUniqueId(&id) != ncclSuccess) return DPP_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out128, &id, 128);
+  return DPP_OK;
+}
+
+int dpp_comm_init(dpp_handle ctx, int rank, int world, const void* unique_id, int64_t owned_begin, int64_t owned_end) {
+  if (!ctx || world < 1 || rank < 0 || rank >= world || owned_begin < 0 || owned_end > ctx->n_nodes || owned_begin > owned_end) {
+    if (ctx) ctx->set_error("dpp_comm_init: invalid argument");
+    return DPP_ERR_INVALID;
+  }
+  cudaSetDevice(ctx->device);
+  dpp::comm_destroy(ctx);
+  ctx->rank = rank;
+  ctx->world = world;
+  ctx->owned_begin = owned_begin;
+  ctx->owned_end = owned_end;
+  ctx->invalidate();
+  if (world == 1) return DPP_OK;
+  if (!unique_id) {
+    ctx->set_error("dpp_comm_init: nccl_unique_id required for world > 1");
+    return DPP_ERR_INVALID;
+  }
+  if (!dpp::nccl().ok) {
+    ctx->set_error(dpp::nccl().error);
+    return DPP_ERR_NCCL;
+  }
+  using dpp::nccl;
+  ctx->comm = new dpp::Comm();
+  ncclUniqueId id;
+  memcpy(&id, unique_id, 128);
+  DPP_NCCL(nccl().CommInitRank(&ctx->comm->comm, world, id, rank));
+  return DPP_OK;
+}
+
+int dpp_comm_add_neighbor(dpp_handle ctx, int peer, int64_t n_send, const int32_t* send_nodes, int64_t n_recv,
+                          const int32_t* recv_nodes) {
+  if (!ctx || !ctx->comm || peer < 0 || peer >= ctx->world || peer == ctx->rank) {
+    if (ctx) ctx->set_error("dpp_comm_add_neighbor: invalid argument or dpp_comm_init not called");
+    return DPP_ERR_INVALID;
+  }
+  cudaSetDevice(ctx->device);
+  dpp::Neighbor nb;
+  nb.peer = peer;
+  nb.n_send = n_send;
+  nb.n_recv = n_recv;
+  if (n_send > 0) {
+    nb.send_contig = dpp::contiguous(send_nodes, n_send);
+    nb.send0 = send_nodes[0];
+    DPP_CHECK(dpp::dev_alloc(ctx, &nb.d_send_idx, n_send));
+    DPP_CHECK(dpp::dev_alloc(ctx, &nb.d_sendbuf, 2 * n_send));
+    DPP_CUDA(cudaMemcpy(nb.d_send_idx, send_nodes, sizeof(int32_t) * n_send, cudaMemcpyHostToDevice));
+  }
+  if (n_recv > 0) {
+    nb.recv_contig = dpp::contiguous(recv_nodes, n_recv);
+    nb.recv0 = recv_nodes[0];
+    DPP_CHECK(dpp::dev_alloc(ctx, &nb.d_recv_idx, n_recv));
+    DPP_CHECK(dpp::dev_alloc(ctx, &nb.d_recvbuf, 2 * n_recv));
+    DPP_CUDA(cudaMemcpy(nb.d_recv_idx, recv_nodes, sizeof(int32_t) * n_recv, cudaMemcpyHostToDevice));
+  }
+  ctx->comm->nbrs.push_back(nb);
+  return DPP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+// Internal declarations shared by the translation units of libdppb200.so.
+// Nothing here crosses the C ABI (include/dpp_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dpp_b200.h"
+
+#define DPP_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      ctx->set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                     std::to_string(__LINE__) + ")");                                           \
+      return DPP_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define DPP_CHECK(expr)                  \
+  do {                                   \
+    int rc__ = (expr);                   \
+    if (rc__ != DPP_OK) return rc__;     \
+  } while (0)
+
+namespace dpp {
+
+constexpr int kMaxBand = 5;  // 2*P+1 for P<=2
+
+// y_f = sum_g (cK[f][g] K + cM[f][g] M) x_g  : the 2x2 block structure of dpp_form
+struct Coef {
+  double cK[2][2];
+  double cM[2][2];
+};
+
+// One application of a (block of the) DPP operator with Firedrake DirichletBC semantics.
+struct OpArgs {
+  int nf;                      // 1 or 2 fields
+  const double* x[2];
+  double* y[2];
+  const uint8_t* in_mask[2];   // !=0 -> input treated as 0 (column elimination); may be null
+  const uint8_t* out_mask[2];  // !=0 -> row replaced (row elimination); may be null
+  int identity_on_masked;      // 1: y = x on eliminated rows (diagonal 1); 0: y = 0
+  Coef c;
+  double* dot_partials;        // optional: per-block partial sums of sum_f <x_f, y_f> over owned rows
+  int64_t owned_begin, owned_end;  // rows (local node ids) to compute
+  const double* skip_flag;     // optional device scalar: != 0 -> the launch is a no-op
+};
+
+// Tensor-grid description for the structured family. Axis 0 = x (slowest), 2 = z (contiguous).
+// 2-D meshes are stored with a 1-node dummy axis 0 (m = 1, k = 0).
+struct GridDesc {
+  int n[3];                 // nodes per axis
+  int band;                 // P: half bandwidth of the 1-D matrices (degree)
+  const double* m1d[3];     // device: [n[a]][2P+1] assembled 1-D mass rows (zero outside domain)
+  const double* k1d[3];     // device: [n[a]][2P+1] assembled 1-D stiffness rows
+};
+
+struct Krylov;  // krylov.cu
+struct CsrMatrix;
+struct Comm;
+
+}  // namespace dpp
+
+struct dpp_context {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int64_t device_bytes = 0;
+
+  // mesh
+  int dim = 0, degree = 0, npc = 0, nvc = 0;
+  int64_t n_nodes = 0, n_cells = 0, n_coord_nodes = 0;
+  int32_t* d_cnm = nullptr;       // [n_cells*npc]
+  double* d_coords = nullptr;     // [n_coord_nodes*dim]
+  int32_t* d_ccnm = nullptr;      // [n_cells*nvc] (aliases d_cnm when degree==1 and same array)
+  bool ccnm_alias = false;
+
+  // kernel family
+  int family = DPP_KERNEL_GENERAL;
+  bool structured_ok = false;
+  dpp::GridDesc grid{};
+  double* d_tables = nullptr;     // backing store of grid.m1d/k1d
+  std::vector<double> h_axis[3];  // 1-D vertex coordinates per axis (structured)
+
+  // general family: node -> (cell, local index) adjacency, per-cell geometry
+  int64_t* d_adj_ptr = nullptr;   // [n_nodes+1]
+  int32_t* d_adj = nullptr;       // packed cell*32 + local   (cell < 2^26) or two arrays; see apply_general.cu
+  int32_t* d_adj_cell = nullptr;
+  uint8_t* d_adj_loc = nullptr;
+  double* d_cell_geom = nullptr;  // [n_cells*8]: affine metric (6) + detJ + flag
+  bool general_ready = false;
+
+  // parameters
+  bool have_params = false;
+  double k1 = 0, k2 = 0, beta = 0, mu = 1;
+
+  // Dirichlet data
+  uint8_t* d_mask = nullptr;      // [2*n_nodes]
+  double* d_g = nullptr;          // [2*n_nodes]  (0 where unconstrained)
+  bool have_bc[2] = {false, false};
+
+  // partition
+  int rank = 0, world = 1;
+  int64_t owned_begin = 0, owned_end = 0;
+  dpp::Comm* comm = nullptr;
+
+  // work vectors / solver state (krylov.cu)
+  dpp::Krylov* krylov = nullptr;
+  dpp::CsrMatrix* csr = nullptr;
+  double* d_solution = nullptr;   // [2*n_nodes]
+  double* d_diag = nullptr;       // [2*n_nodes] diag(A_bc), valid when diag_valid
+  bool diag_valid = false;
+
+  // reduction scratch
+  double* d_partials = nullptr;   // [kMaxPartialBlocks * kMaxDotWidth]
+  double* d_scalars = nullptr;    // device scalar block
+  double* h_scalars = nullptr;    // pinned mirror
+  double* d_hist[2] = {nullptr, nullptr};  // residual history per solver slot
+  int hist_cap[2] = {0, 0};
+
+  void set_error(const std::string& s) { err = s; }
+  void invalidate() { diag_valid = false; }
+};
+
+namespace dpp {
+
+constexpr int kMaxPartialBlocks = 4096;
+constexpr int kMaxDotWidth = 40;   // >= gmres restart + 2
+constexpr int kNumScalars = 256;
+
+// ---- apply_structured.cu
+int structured_detect_and_setup(dpp_context* ctx, const int32_t* cnm_host, const double* coords_host,
+                                const int32_t* ccnm_host);
+int structured_apply(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks);
+int structured_diagonal(dpp_context* ctx, const Coef& c, double* d_diag /*[2*n_nodes]*/);
+
+// ---- apply_general.cu
+int general_setup(dpp_context* ctx, const int32_t* cnm_host);
+int general_apply(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks);
+int general_diagonal(dpp_context* ctx, const Coef& c, double* d_diag);
+
+// ---- operator.cu : dispatch + DPP coefficient blocks
+Coef dpp_coef(const dpp_context* ctx);                    // monolithic 2x2
+Coef block_coef(const dpp_context* ctx, int row, int col); // single block as nf=1 coefficient
+int op_apply(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks);
+int op_diagonal(dpp_context* ctx);                        // fills ctx->d_diag with diag(A_bc)
+
+// ---- vector_ops.cu
+int vec_zero(dpp_context* ctx, double* x, int64_t n);
+int vec_copy(dpp_context* ctx, double* dst, const double* src, int64_t n);
+
+// ---- comm.cu
+int comm_halo_exchange(dpp_context* ctx, double* const* fields, int nf);
+int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n);
+void comm_destroy(dpp_context* ctx);
+
+// ---- assemble_csr.cu
+int csr_assemble(dpp_context* ctx, int64_t* nnz);
+int csr_export(dpp_context* ctx, int64_t* indptr, int32_t* indices, double* data);
+int csr_spmv(dpp_context* ctx, const double* x, double* y, double* dot_partials, int* n_partial_blocks);
+void csr_destroy(dpp_context* ctx);
+
+// ---- krylov.cu
+int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_result* res,
+                 double* hist_host, int32_t hist_cap);
+void krylov_destroy(dpp_context* ctx);
+
+template <typename T>
+inline int dev_alloc(dpp_context* ctx, T** p, int64_t count) {
+  size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void**)p, bytes);
+  if (e != cudaSuccess) {
+    ctx->set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    return DPP_ERR_CUDA;
+  }
+  ctx->device_bytes += (int64_t)bytes;
+  return DPP_OK;
+}
+
+}  // namespace dpp

@@ -1,0 +1,605 @@
+// Krylov layer: what PETSc KSP/PC does under solver.solve() (solvers/solver.py:71) for the DPP
+// system -- KSPCG (preconditioned norm), KSPGMRES (left PC, classical Gram-Schmidt, restart),
+// PCJACOBI / point-block Jacobi / PCFIELDSPLIT (additive, multiplicative), and the
+// scale-splitting block Picard iteration on the dpp_delayed_form split (forms/dpp.py:135-205).
+// Semantics follow SURVEY Appendix A.3-A.6; tests/ compare against the CPU restatement.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "vector_ops.cuh"
+
+namespace dpp {
+
+struct Krylov {
+  int64_t nvec = 0;  // 2 * n_nodes
+  double *b = nullptr, *x = nullptr, *r = nullptr, *p = nullptr, *w = nullptr, *z = nullptr, *t = nullptr;
+  double *u0 = nullptr;
+  // single-field work vectors for block solves
+  double *bi = nullptr, *xi = nullptr, *ri = nullptr, *pi = nullptr, *wi = nullptr, *zi = nullptr;
+  double *dinv = nullptr;        // 1/diag(A_bc)  [2n]
+  double *pb = nullptr;          // point-block inverse: i00,i01,i11  [3n]
+  bool pb_valid = false;
+  std::vector<double*> V;        // GMRES basis
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t inner_its = 0;
+  int64_t apply_count = 0;
+};
+
+namespace {
+
+struct OpSpec {
+  int nf;      // 2: monolithic A_bc ; 1: block (row,col)
+  int row, col;
+  int mode;    // dpp_operator_mode
+};
+
+struct Tol {
+  double rtol, atol, dtol;
+  int max_it;
+};
+
+struct KspOut {
+  int its = 0;
+  int reason = 0;
+  double rnorm = 0.0;
+  std::vector<double> hist;
+};
+
+__global__ void k_reciprocal(long long n, const double* __restrict__ d, double* __restrict__ o) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    o[i] = 1.0 / d[i];
+}
+
+__global__ void k_pb_blocks(long long n, const double* __restrict__ diag, const double* __restrict__ mdiag,
+                            const uint8_t* __restrict__ mask, double boff, double* __restrict__ pb) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = diag[i], c = diag[n + i];
+    const double b = (mask[i] || mask[n + i]) ? 0.0 : boff * mdiag[i];
+    const double det = a * c - b * b;
+    pb[i] = c / det;
+    pb[n + i] = -b / det;
+    pb[2 * n + i] = a / det;
+  }
+}
+
+__global__ void k_sub(long long n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ o) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    o[i] = a[i] - b[i];
+}
+
+int ew_blocks(const dpp_context* ctx, long long n) {
+  return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16));
+}
+
+VecLayout layout(const dpp_context* ctx, int nf) {
+  return VecLayout{nf, ctx->n_nodes, ctx->owned_begin, ctx->owned_end};
+}
+
+// y = Op x ; optional fused <x,y> partials ; x/y are base pointers (field stride n_nodes)
+int apply_spec(dpp_context* ctx, const OpSpec& op, const double* x, double* y, bool want_dot, const double* skip,
+               int* nblocks) {
+  const int64_t n = ctx->n_nodes;
+  if (op.mode == DPP_OP_ASSEMBLED) {
+    if (op.nf != 2) {
+      ctx->set_error("assembled operator mode supports the monolithic operator only");
+      return DPP_ERR_INVALID;
+    }
+    ctx->krylov->apply_count++;
+    return csr_spmv(ctx, x, y, want_dot ? ctx->d_partials : nullptr, nblocks);
+  }
+  OpArgs a{};
+  a.nf = op.nf;
+  a.identity_on_masked = 1;
+  a.owned_begin = ctx->owned_begin;
+  a.owned_end = ctx->owned_end;
+  a.dot_partials = want_dot ? ctx->d_partials : nullptr;
+  a.skip_flag = skip;
+  if (op.nf == 2) {
+    a.c = dpp_coef(ctx);
+    for (int f = 0; f < 2; ++f) {
+      a.x[f] = x + f * n;
+      a.y[f] = y + f * n;
+      a.in_mask[f] = a.out_mask[f] = ctx->d_mask + f * n;
+    }
+  } else {
+    a.c = block_coef(ctx, op.row, op.col);
+    a.x[0] = x;
+    a.y[0] = y;
+    a.in_mask[0] = ctx->d_mask + op.col * n;
+    a.out_mask[0] = ctx->d_mask + op.row * n;
+    a.identity_on_masked = (op.row == op.col) ? 1 : 0;
+  }
+  ctx->krylov->apply_count++;
+  return op_apply(ctx, a, nblocks);
+}
+
+int halo(dpp_context* ctx, double* x, int nf) {
+  if (ctx->world <= 1) return DPP_OK;
+  double* f[2] = {x, x + ctx->n_nodes};
+  return comm_halo_exchange(ctx, f, nf);
+}
+
+// ------------------------------------------------------------------------------------------------
+// KSPCG with fused Jacobi / no preconditioner: the whole iteration runs from device scalars, the
+// host polls the converged flag every `check_every` iterations (kernels launched past convergence
+// are no-ops, so the reported iteration count is exact).
+// ------------------------------------------------------------------------------------------------
+struct CgWork {
+  double *r, *p, *w, *z;
+};
+
+struct Pc;  // fwd
+int pc_apply(dpp_context* ctx, Pc& pc, const double* r, double* z);
+
+struct Pc {
+  int type = DPP_PC_NONE;
+  const double* dinv = nullptr;  // Jacobi (fusable)
+  const dpp_options* opt = nullptr;
+  bool fusable() const { return type == DPP_PC_NONE || type == DPP_PC_JACOBI; }
+};
+
+int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* x, CgWork wk, const Tol& tol, int slot,
+           int check_every, int hist_cap, KspOut* out) {
+  const VecLayout L = layout(ctx, op.nf);
+  const int64_t len = (int64_t)op.nf * ctx->n_nodes;
+  const bool fused = pc.fusable();
+  const double* dinv = (pc.type == DPP_PC_JACOBI) ? pc.dinv : nullptr;
+  double* S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
+  if (hist_cap > ctx->hist_cap[slot]) {
+    if (ctx->d_hist[slot]) cudaFree(ctx->d_hist[slot]);
+    ctx->d_hist[slot] = nullptr;
+    DPP_CHECK(dev_alloc(ctx, &ctx->d_hist[slot], hist_cap));
+    ctx->hist_cap[slot] = hist_cap;
+  }
+  DPP_CHECK(scalars_init(ctx, slot, tol.rtol, tol.atol, tol.dtol, tol.max_it, std::min(hist_cap, ctx->hist_cap[slot])));
+  DPP_CHECK(vec_zero(ctx, x, len));
+  DPP_CHECK(vec_copy(ctx, wk.r, b, len));
+  if (fused) {
+    DPP_CHECK(vec_pointwise_mult(ctx, L, dinv, wk.r, wk.z));
+  } else {
+    DPP_CHECK(pc_apply(ctx, pc, wk.r, wk.z));
+  }
+  DPP_CHECK(vec_dot2(ctx, L, wk.r, wk.z, wk.z, wk.z, slot, POST_CG_INIT));
+  const double* h = ctx->h_scalars + (size_t)slot * S_SLOT_SIZE;
+  DPP_CHECK(scalars_fetch(ctx, slot));
+  const int every = fused ? std::max(1, check_every) : 1;
+  while (h[S_REASON] == 0.0) {
+    for (int k = 0; k < every; ++k) {
+      DPP_CHECK(cg_p_update(ctx, L, wk.p, wk.r, dinv, fused ? nullptr : wk.z, slot));
+      DPP_CHECK(halo(ctx, wk.p, op.nf));
+      int nb = 0;
+      DPP_CHECK(apply_spec(ctx, op, wk.p, wk.w, true, S + S_REASON, &nb));
+      DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
+      DPP_CHECK(cg_xr_update(ctx, L, x, wk.r, wk.p, wk.w, dinv, fused, slot, POST_CG_RZ));
+      if (!fused) {
+        DPP_CHECK(pc_apply(ctx, pc, wk.r, wk.z));
+        DPP_CHECK(vec_dot2(ctx, L, wk.r, wk.z, wk.z, wk.z, slot, POST_CG_RZ));
+      }
+    }
+    DPP_CHECK(scalars_fetch(ctx, slot));
+  }
+  out->its = (int)h[S_ITS];
+  out->reason = (int)h[S_REASON];
+  out->rnorm = h[S_RNORM];
+  const int nh = std::min(out->its + 1, std::min(hist_cap, ctx->hist_cap[slot]));
+  out->hist.resize(std::max(nh, 0));
+  if (nh > 0) {
+    DPP_CUDA(cudaMemcpyAsync(out->hist.data(), ctx->d_hist[slot], sizeof(double) * nh, cudaMemcpyDeviceToHost, ctx->stream));
+    DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return DPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Preconditioners
+// ------------------------------------------------------------------------------------------------
+int solve_block(dpp_context* ctx, const dpp_options* opt, int f, const double* rhs, double* out) {
+  Krylov* K = ctx->krylov;
+  const int64_t n = ctx->n_nodes;
+  const VecLayout L1 = layout(ctx, 1);
+  const double* dinv_f = (opt->inner_pc_type == DPP_PC_JACOBI) ? K->dinv + f * n : nullptr;
+  if (opt->inner_ksp_type == DPP_INNER_PREONLY) return vec_pointwise_mult(ctx, L1, dinv_f, rhs, out);
+  OpSpec op{1, f, f, DPP_OP_MATRIX_FREE};
+  Pc pc;
+  pc.type = dinv_f ? DPP_PC_JACOBI : DPP_PC_NONE;
+  pc.dinv = dinv_f;
+  Tol tol{opt->inner_rtol, opt->inner_atol, opt->dtol, opt->inner_max_it};
+  KspOut o;
+  CgWork wk{K->ri, K->pi, K->wi, K->zi};
+  DPP_CHECK(cg_run(ctx, op, pc, rhs, out, wk, tol, 1, opt->check_every, 0, &o));
+  K->inner_its += o.its;
+  return DPP_OK;
+}
+
+// out = rhs_row - A[row][col] xcol     (off-diagonal block: P_row (-beta/mu M) P_col)
+int coupled_rhs(dpp_context* ctx, int row, int col, const double* rhs_row, double* xcol, double* out, double* tmp) {
+  OpSpec op{1, row, col, DPP_OP_MATRIX_FREE};
+  DPP_CHECK(halo(ctx, xcol, 1));
+  int nb = 0;
+  DPP_CHECK(apply_spec(ctx, op, xcol, tmp, false, nullptr, &nb));
+  k_sub<<<ew_blocks(ctx, ctx->n_nodes), 256, 0, ctx->stream>>>(ctx->n_nodes, rhs_row, tmp, out);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+
+int pc_apply(dpp_context* ctx, Pc& pc, const double* r, double* z) {
+  Krylov* K = ctx->krylov;
+  const int64_t n = ctx->n_nodes;
+  const VecLayout L2 = layout(ctx, 2);
+  switch (pc.type) {
+    case DPP_PC_NONE:
+      return vec_copy(ctx, z, r, 2 * n);
+    case DPP_PC_JACOBI:
+      return vec_pointwise_mult(ctx, L2, pc.dinv, r, z);
+    case DPP_PC_PBJACOBI:
+      return vec_pbjacobi(ctx, L2, K->pb, K->pb + n, K->pb + 2 * n, r, z);
+    case DPP_PC_FIELDSPLIT: {
+      // y0 = A00^-1 r0 ; y1 = A11^-1 (r1 - A10 y0)  [multiplicative]  (solvers/parameters.py:30-57)
+      DPP_CHECK(solve_block(ctx, pc.opt, 0, r, z));
+      const double* rhs1 = r + n;
+      if (pc.opt->fieldsplit_type == DPP_FS_MULTIPLICATIVE) {
+        DPP_CHECK(coupled_rhs(ctx, 1, 0, r + n, z, K->bi, K->xi));
+        rhs1 = K->bi;
+      }
+      return solve_block(ctx, pc.opt, 1, rhs1, z + n);
+    }
+  }
+  ctx->set_error("unknown pc_type");
+  return DPP_ERR_INVALID;
+}
+
+int pc_setup(dpp_context* ctx, const dpp_options* opt, Pc* pc) {
+  Krylov* K = ctx->krylov;
+  const int64_t n = ctx->n_nodes;
+  pc->type = opt->pc_type;
+  pc->opt = opt;
+  const bool need_diag = opt->pc_type == DPP_PC_JACOBI || opt->pc_type == DPP_PC_PBJACOBI ||
+                         ((opt->pc_type == DPP_PC_FIELDSPLIT || opt->ksp_type == DPP_KSP_PICARD) &&
+                          opt->inner_pc_type == DPP_PC_JACOBI);
+  if (need_diag) {
+    if (!ctx->diag_valid) {
+      DPP_CHECK(op_diagonal(ctx));
+      k_reciprocal<<<ew_blocks(ctx, 2 * n), 256, 0, ctx->stream>>>(2 * n, ctx->d_diag, K->dinv);
+      ctx->launches++;
+      DPP_CUDA(cudaGetLastError());
+      ctx->diag_valid = true;
+      K->pb_valid = false;
+    }
+    pc->dinv = K->dinv;
+  }
+  if (opt->pc_type == DPP_PC_PBJACOBI && !K->pb_valid) {
+    if (!K->pb) DPP_CHECK(dev_alloc(ctx, &K->pb, 3 * n));
+    // nodal mass diagonal (no masking) into K->t
+    Coef cm{};
+    cm.cM[0][0] = 1.0;
+    cm.cM[1][1] = 1.0;
+    const uint8_t* save = ctx->d_mask;
+    ctx->d_mask = nullptr;
+    int rc = (ctx->family == DPP_KERNEL_STRUCTURED) ? structured_diagonal(ctx, cm, K->t) : general_diagonal(ctx, cm, K->t);
+    ctx->d_mask = const_cast<uint8_t*>(save);
+    DPP_CHECK(rc);
+    k_pb_blocks<<<ew_blocks(ctx, n), 256, 0, ctx->stream>>>(n, ctx->d_diag, K->t, ctx->d_mask, -ctx->beta / ctx->mu, K->pb);
+    ctx->launches++;
+    DPP_CUDA(cudaGetLastError());
+    K->pb_valid = true;
+  }
+  return DPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KSPGMRES(m): left preconditioning, classical Gram-Schmidt, Givens residual recurrence
+// ------------------------------------------------------------------------------------------------
+struct DefaultTest {
+  double rtol, atol, dtol, rnorm0 = 0, ttol = 0;
+  int operator()(int its, double rnorm) {
+    if (its == 0) {
+      rnorm0 = rnorm;
+      ttol = std::max(rtol * rnorm, atol);
+    }
+    if (!std::isfinite(rnorm)) return DPP_DIVERGED_NANORINF;
+    if (rnorm <= ttol) return rnorm < atol ? DPP_CONVERGED_ATOL : DPP_CONVERGED_RTOL;
+    if (rnorm >= dtol * rnorm0) return DPP_DIVERGED_DTOL;
+    return 0;
+  }
+};
+
+int norm2_host(dpp_context* ctx, const VecLayout& L, const double* v, int slot, double* out) {
+  DPP_CHECK(vec_dot2(ctx, L, v, v, nullptr, nullptr, slot, POST_NONE));
+  DPP_CHECK(scalars_fetch(ctx, slot));
+  *out = std::sqrt(ctx->h_scalars[(size_t)slot * S_SLOT_SIZE + S_TMP]);
+  return DPP_OK;
+}
+
+int gmres_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* x, const Tol& tol, int restart,
+              KspOut* out) {
+  Krylov* K = ctx->krylov;
+  const VecLayout L = layout(ctx, 2);
+  const int64_t len = 2 * ctx->n_nodes;
+  const int slot = 0;
+  restart = std::max(1, std::min(restart, 30));
+  while ((int)K->V.size() < restart + 1) {
+    double* v = nullptr;
+    DPP_CHECK(dev_alloc(ctx, &v, len));
+    DPP_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * len, ctx->stream));
+    K->V.push_back(v);
+  }
+  DefaultTest test{tol.rtol, tol.atol, tol.dtol};
+  const double* h = ctx->h_scalars + (size_t)slot * S_SLOT_SIZE;
+  DPP_CHECK(vec_zero(ctx, x, len));
+  int its = 0, reason = 0;
+  double res = 0.0;
+  bool first = true;
+  std::vector<double> H((size_t)(restart + 2) * (restart + 1)), cc(restart + 1), ss(restart + 1), grs(restart + 2);
+  auto Hm = [&](int r, int c) -> double& { return H[(size_t)r * (restart + 1) + c]; };
+  const bool pc_none = pc.type == DPP_PC_NONE;
+  while (true) {
+    // V0 = M^-1 (b - A x)
+    if (first) {
+      if (pc_none) DPP_CHECK(vec_copy(ctx, K->V[0], b, len));
+      else DPP_CHECK(pc_apply(ctx, pc, b, K->V[0]));
+    } else {
+      DPP_CHECK(halo(ctx, x, 2));
+      int nb = 0;
+      DPP_CHECK(apply_spec(ctx, op, x, K->w, false, nullptr, &nb));
+      DPP_CHECK(vec_axpby(ctx, L, 1.0, b, -1.0, K->w));  // w = b - A x
+      if (pc_none) DPP_CHECK(vec_copy(ctx, K->V[0], K->w, len));
+      else DPP_CHECK(pc_apply(ctx, pc, K->w, K->V[0]));
+    }
+    first = false;
+    DPP_CHECK(norm2_host(ctx, L, K->V[0], slot, &res));
+    out->hist.push_back(res);
+    if (res == 0.0) { reason = DPP_CONVERGED_ATOL; break; }
+    reason = test(its, res);
+    if (reason) break;
+    if (its >= tol.max_it) { reason = DPP_DIVERGED_ITS; break; }
+    DPP_CHECK(vec_scale_into(ctx, L, 1.0 / res, K->V[0], K->V[0]));
+    std::fill(H.begin(), H.end(), 0.0);
+    grs[0] = res;
+    int it = 0;
+    while (!reason && it < restart && its < tol.max_it) {
+      if (it) out->hist.push_back(res);
+      double* vnew = K->V[it + 1];
+      DPP_CHECK(halo(ctx, K->V[it], 2));
+      int nb = 0;
+      if (pc_none) {
+        DPP_CHECK(apply_spec(ctx, op, K->V[it], vnew, false, nullptr, &nb));
+      } else {
+        DPP_CHECK(apply_spec(ctx, op, K->V[it], K->w, false, nullptr, &nb));
+        DPP_CHECK(pc_apply(ctx, pc, K->w, vnew));
+      }
+      DPP_CHECK(gmres_mdot(ctx, L, K->V.data(), it + 1, vnew, slot));
+      DPP_CHECK(gmres_maxpy_norm(ctx, L, K->V.data(), it + 1, vnew, slot));
+      DPP_CHECK(scalars_fetch(ctx, slot));
+      const double tt = std::sqrt(h[S_TMP + kGmresNormOffset]);
+      bool hapend = false;
+      const double hapbnd = std::min(std::fabs(tt / grs[it]), 1e-30);
+      if (tt < hapbnd) hapend = true;
+      else DPP_CHECK(vec_scale_into(ctx, L, 1.0 / tt, vnew, vnew));
+      for (int j = 0; j <= it; ++j) Hm(j, it) = h[S_TMP + j];
+      Hm(it + 1, it) = tt;
+      for (int j = 0; j < it; ++j) {
+        const double t = Hm(j, it);
+        Hm(j, it) = cc[j] * t + ss[j] * Hm(j + 1, it);
+        Hm(j + 1, it) = cc[j] * Hm(j + 1, it) - ss[j] * t;
+      }
+      if (!hapend) {
+        const double t = std::sqrt(Hm(it, it) * Hm(it, it) + Hm(it + 1, it) * Hm(it + 1, it));
+        if (t == 0.0) { reason = DPP_DIVERGED_BREAKDOWN; break; }
+        cc[it] = Hm(it, it) / t;
+        ss[it] = Hm(it + 1, it) / t;
+        grs[it + 1] = -ss[it] * grs[it];
+        grs[it] = cc[it] * grs[it];
+        Hm(it, it) = cc[it] * Hm(it, it) + ss[it] * Hm(it + 1, it);
+        res = std::fabs(grs[it + 1]);
+      } else {
+        res = 0.0;
+      }
+      ++it;
+      ++its;
+      reason = test(its, res);
+      if (hapend && !reason) reason = DPP_DIVERGED_BREAKDOWN;
+    }
+    if (it && (reason || its >= tol.max_it)) out->hist.push_back(res);
+    if (it) {
+      std::vector<double> y(it);
+      for (int k = it - 1; k >= 0; --k) {
+        double s = grs[k];
+        for (int j = k + 1; j < it; ++j) s -= Hm(k, j) * y[j];
+        y[k] = s / Hm(k, k);
+      }
+      DPP_CHECK(vec_maxpy_host(ctx, L, K->V.data(), it, y.data(), x));
+      DPP_CUDA(cudaStreamSynchronize(ctx->stream));  // y is a stack-lifetime host buffer
+    }
+    if (reason) break;
+    if (its >= tol.max_it) { reason = DPP_DIVERGED_ITS; break; }
+  }
+  out->its = its;
+  out->reason = reason;
+  out->rnorm = res;
+  return DPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block Picard (scale splitting), SURVEY A.6
+// ------------------------------------------------------------------------------------------------
+int picard_run(dpp_context* ctx, const dpp_options* opt, const double* b, double* d, const Tol& tol, double bnorm,
+               KspOut* out) {
+  Krylov* K = ctx->krylov;
+  const int64_t n = ctx->n_nodes;
+  const VecLayout L2 = layout(ctx, 2);
+  DPP_CHECK(vec_zero(ctx, d, 2 * n));
+  const double ttol = std::max(tol.rtol * bnorm, tol.atol);
+  double fnorm = bnorm;
+  int its = 0;
+  out->hist.push_back(fnorm);
+  OpSpec mono{2, 0, 0, DPP_OP_MATRIX_FREE};
+  while (fnorm > ttol && its < tol.max_it && std::isfinite(fnorm)) {
+    // (k1K+bM) d0 = b0 - A01 d1
+    DPP_CHECK(coupled_rhs(ctx, 0, 1, b, d + n, K->bi, K->xi));
+    DPP_CHECK(solve_block(ctx, opt, 0, K->bi, K->t));
+    DPP_CHECK(vec_copy(ctx, d, K->t, n));
+    // (k2K+bM) d1 = b1 - A10 d0
+    DPP_CHECK(coupled_rhs(ctx, 1, 0, b + n, d, K->bi, K->xi));
+    DPP_CHECK(solve_block(ctx, opt, 1, K->bi, K->t));
+    DPP_CHECK(vec_copy(ctx, d + n, K->t, n));
+    // monolithic residual
+    DPP_CHECK(halo(ctx, d, 2));
+    int nb = 0;
+    DPP_CHECK(apply_spec(ctx, mono, d, K->w, false, nullptr, &nb));
+    DPP_CHECK(vec_axpby(ctx, L2, 1.0, b, -1.0, K->w));
+    DPP_CHECK(norm2_host(ctx, L2, K->w, 0, &fnorm));
+    out->hist.push_back(fnorm);
+    ++its;
+  }
+  out->its = its;
+  out->rnorm = fnorm;
+  out->reason = !std::isfinite(fnorm) ? DPP_DIVERGED_NANORINF
+                                      : (fnorm <= ttol ? (fnorm < tol.atol ? DPP_CONVERGED_ATOL : DPP_CONVERGED_RTOL)
+                                                       : DPP_DIVERGED_ITS);
+  return DPP_OK;
+}
+
+int ensure_work(dpp_context* ctx) {
+  if (ctx->krylov && ctx->krylov->nvec == 2 * ctx->n_nodes) return DPP_OK;
+  if (!ctx->krylov) ctx->krylov = new Krylov();
+  Krylov* K = ctx->krylov;
+  const int64_t n = ctx->n_nodes;
+  K->nvec = 2 * n;
+  double** two[] = {&K->b, &K->x, &K->r, &K->p, &K->w, &K->z, &K->t, &K->u0, &K->dinv};
+  for (double** v : two) {
+    DPP_CHECK(dev_alloc(ctx, v, 2 * n));
+    DPP_CUDA(cudaMemsetAsync(*v, 0, sizeof(double) * 2 * n, ctx->stream));
+  }
+  double** one[] = {&K->bi, &K->xi, &K->ri, &K->pi, &K->wi, &K->zi};
+  for (double** v : one) {
+    DPP_CHECK(dev_alloc(ctx, v, n));
+    DPP_CUDA(cudaMemsetAsync(*v, 0, sizeof(double) * n, ctx->stream));
+  }
+  for (auto& e : K->ev) DPP_CUDA(cudaEventCreate(&e));
+  return DPP_OK;
+}
+
+}  // namespace
+
+int krylov_work_vectors(dpp_context* ctx, double** a, double** b) {
+  DPP_CHECK(ensure_work(ctx));
+  *a = ctx->krylov->p;
+  *b = ctx->krylov->w;
+  return DPP_OK;
+}
+
+int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_result* res, double* hist_host,
+                 int32_t hist_cap) {
+  if (!ctx->have_params) {
+    ctx->set_error("dpp_solve: call dpp_set_params first");
+    return DPP_ERR_STATE;
+  }
+  DPP_CHECK(ensure_work(ctx));
+  Krylov* K = ctx->krylov;
+  const int64_t n = ctx->n_nodes;
+  const VecLayout L2 = layout(ctx, 2);
+  K->inner_its = 0;
+  K->apply_count = 0;
+  if (opt->operator_mode == DPP_OP_ASSEMBLED && ctx->csr == nullptr) {
+    int64_t nnz = 0;
+    DPP_CHECK(csr_assemble(ctx, &nnz));
+  }
+  DPP_CUDA(cudaEventRecord(K->ev[0], ctx->stream));
+  // lifting: u0 = g on Gamma; b = -(A u0) on interior rows, 0 on Gamma
+  {
+    OpArgs a{};
+    a.nf = 2;
+    a.c = dpp_coef(ctx);
+    for (int f = 0; f < 2; ++f)
+      for (int g = 0; g < 2; ++g) {
+        a.c.cK[f][g] = -a.c.cK[f][g];
+        a.c.cM[f][g] = -a.c.cM[f][g];
+      }
+    for (int f = 0; f < 2; ++f) {
+      a.x[f] = ctx->d_g + f * n;
+      a.y[f] = K->b + f * n;
+      a.in_mask[f] = nullptr;
+      a.out_mask[f] = ctx->d_mask + f * n;
+    }
+    a.identity_on_masked = 0;
+    a.owned_begin = ctx->owned_begin;
+    a.owned_end = ctx->owned_end;
+    int nb = 0;
+    DPP_CHECK(op_apply(ctx, a, &nb));
+  }
+  double bnorm = 0.0;
+  DPP_CHECK(norm2_host(ctx, L2, K->b, 0, &bnorm));
+  Pc pc;
+  DPP_CHECK(pc_setup(ctx, opt, &pc));
+  DPP_CUDA(cudaEventRecord(K->ev[1], ctx->stream));
+
+  Tol tol{opt->rtol, opt->atol, opt->dtol, opt->max_it};
+  OpSpec mono{2, 0, 0, opt->operator_mode};
+  KspOut out;
+  int rc = DPP_OK;
+  switch (opt->ksp_type) {
+    case DPP_KSP_CG: {
+      CgWork wk{K->r, K->p, K->w, K->z};
+      rc = cg_run(ctx, mono, pc, K->b, K->x, wk, tol, 0, opt->check_every, std::max(hist_cap, 0), &out);
+      break;
+    }
+    case DPP_KSP_GMRES:
+      rc = gmres_run(ctx, mono, pc, K->b, K->x, tol, opt->gmres_restart, &out);
+      break;
+    case DPP_KSP_PICARD:
+      rc = picard_run(ctx, opt, K->b, K->x, tol, bnorm, &out);
+      break;
+    default:
+      ctx->set_error("unknown ksp_type");
+      rc = DPP_ERR_INVALID;
+  }
+  DPP_CHECK(rc);
+  DPP_CUDA(cudaEventRecord(K->ev[2], ctx->stream));
+  // u = u0 + d
+  if (!ctx->d_solution) DPP_CHECK(dev_alloc(ctx, &ctx->d_solution, 2 * n));
+  DPP_CHECK(vec_copy(ctx, ctx->d_solution, ctx->d_g, 2 * n));
+  DPP_CHECK(vec_axpby(ctx, L2, 1.0, K->x, 1.0, ctx->d_solution));
+  if (u_host) {
+    DPP_CUDA(cudaMemcpyAsync(u_host, ctx->d_solution, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms_setup = 0, ms_solve = 0;
+  cudaEventElapsedTime(&ms_setup, K->ev[0], K->ev[1]);
+  cudaEventElapsedTime(&ms_solve, K->ev[1], K->ev[2]);
+  if (res) {
+    res->iterations = out.its;
+    res->converged_reason = out.reason;
+    res->inner_iterations = (int32_t)K->inner_its;
+    res->residual_norm = out.rnorm;
+    res->rhs_norm = bnorm;
+    res->solve_ms = ms_solve;
+    res->setup_ms = ms_setup;
+    res->apply_ms = 0.0;
+    res->apply_count = K->apply_count;
+    res->history_len = 0;
+    if (hist_host && hist_cap > 0) {
+      const int nh = (int)std::min<size_t>(out.hist.size(), (size_t)hist_cap);
+      std::memcpy(hist_host, out.hist.data(), sizeof(double) * nh);
+      res->history_len = nh;
+    }
+  }
+  return DPP_OK;
+}
+
+void krylov_destroy(dpp_context* ctx) {
+  Krylov* K = ctx->krylov;
+  if (!K) return;
+  double* vs[] = {K->b, K->x, K->r, K->p, K->w, K->z, K->t, K->u0, K->dinv, K->bi, K->xi, K->ri, K->pi, K->wi, K->zi, K->pb};
+  for (double* v : vs)
+    if (v) cudaFree(v);
+  for (double* v : K->V) cudaFree(v);
+  for (auto& e : K->ev)
+    if (e) cudaEventDestroy(e);
+  delete K;
+  ctx->krylov = nullptr;
+}
+
+}  // namespace dpp

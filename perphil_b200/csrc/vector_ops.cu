@@ -1,0 +1,445 @@
+// See vector_ops.cuh.  HBM-bound streaming kernels: grid = (blocks, nf), each block walks a
+// contiguous chunk of one field with 4 independent 8-byte loads in flight per thread per array.
+#include <algorithm>
+#include <cmath>
+
+#include "vector_ops.cuh"
+
+namespace dpp {
+
+namespace {
+
+constexpr int VT = 256;   // threads per block
+constexpr int UNROLL = 4;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum in a fixed order; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* sm /*[VT/32]*/) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < VT / 32; ++w) t += sm[w];
+  }
+  return t;
+}
+
+struct Chunk {
+  long long begin, end;  // element range inside the field (absolute index into the array)
+};
+
+__device__ __forceinline__ Chunk my_chunk(const VecLayout& L) {
+  const long long nown = L.oe - L.ob;
+  const long long per = (nown + gridDim.x - 1) / gridDim.x;
+  const long long b = (long long)blockIdx.x * per;
+  const long long e = b + per < nown ? b + per : nown;
+  const long long base = (long long)blockIdx.y * L.stride + L.ob;
+  return Chunk{base + b, base + (e > b ? e : b)};
+}
+
+__device__ void apply_post(double* S, double* hist, int post) {
+  // executed by one thread after the reduction values are in S[S_TMP..]
+  if (post == POST_CG_PAP) {
+    const double pap = S[S_TMP];
+    S[S_PAP] = pap;
+    if (S[S_REASON] == 0.0 && !(pap > 0.0)) S[S_REASON] = (pap == pap) ? DPP_DIVERGED_INDEFINITE_MAT : DPP_DIVERGED_NANORINF;
+    return;
+  }
+  if (post == POST_CG_INIT || post == POST_CG_RZ) {
+    if (S[S_REASON] != 0.0) return;
+    const double rz = S[S_TMP], zz = S[S_TMP + 1];
+    const double rnorm = sqrt(zz);
+    int its;
+    if (post == POST_CG_INIT) {
+      its = 0;
+      S[S_RZ_OLD] = 1.0;
+      S[S_RNORM0] = rnorm;
+      const double t = S[S_RTOL] * rnorm;
+      S[S_TTOL] = t > S[S_ATOL] ? t : S[S_ATOL];
+    } else {
+      its = (int)S[S_ITS] + 1;
+      S[S_RZ_OLD] = S[S_RZ];
+    }
+    S[S_RZ] = rz;
+    S[S_ZZ] = zz;
+    S[S_RNORM] = rnorm;
+    S[S_ITS] = (double)its;
+    if (hist != nullptr && its < (int)S[S_HISTCAP]) hist[its] = rnorm;
+    // KSPConvergedDefault
+    double reason = 0.0;
+    if (!(rnorm == rnorm) || isinf(rnorm)) reason = DPP_DIVERGED_NANORINF;
+    else if (rnorm <= S[S_TTOL]) reason = (rnorm < S[S_ATOL]) ? DPP_CONVERGED_ATOL : DPP_CONVERGED_RTOL;
+    else if (rnorm >= S[S_DTOL] * S[S_RNORM0]) reason = DPP_DIVERGED_DTOL;
+    else if (rz == 0.0) reason = DPP_CONVERGED_ATOL;
+    else if (its >= (int)S[S_MAXIT]) reason = DPP_DIVERGED_ITS;
+    S[S_REASON] = reason;
+  }
+}
+
+__global__ void __launch_bounds__(VT) k_reduce_partials(const double* __restrict__ partials, int nblocks, int width,
+                                                         double* S, double* hist, int post, int do_post,
+                                                         int out_offset) {
+  __shared__ double sm[VT / 32];
+  for (int w = 0; w < width; ++w) {
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += VT) v += partials[(size_t)b * width + w];
+    const double t = block_sum(v, sm);
+    if (threadIdx.x == 0) S[S_TMP + out_offset + w] = t;
+  }
+  if (threadIdx.x == 0 && do_post) apply_post(S, hist, post);
+}
+
+__global__ void k_post_only(double* S, double* hist, int post) { apply_post(S, hist, post); }
+
+__global__ void __launch_bounds__(VT) k_axpby(VecLayout L, double a, const double* x, double b, double* y) {
+  const Chunk c = my_chunk(L);
+  for (long long i = c.begin + threadIdx.x; i < c.end; i += VT) {
+    const double yv = (b == 0.0) ? 0.0 : b * y[i];
+    y[i] = fma(a, x[i], yv);
+  }
+}
+
+__global__ void __launch_bounds__(VT) k_pointwise(VecLayout L, const double* __restrict__ d, const double* __restrict__ r,
+                                                   double* __restrict__ z) {
+  const Chunk c = my_chunk(L);
+  for (long long i = c.begin + threadIdx.x; i < c.end; i += VT) z[i] = d ? d[i] * r[i] : r[i];
+}
+
+__global__ void __launch_bounds__(VT) k_pbjacobi(VecLayout L, const double* __restrict__ i00, const double* __restrict__ i01,
+                                                  const double* __restrict__ i11, const double* __restrict__ r,
+                                                  double* __restrict__ z) {
+  // blockIdx.y ignored: node loop handles both fields
+  const long long nown = L.oe - L.ob;
+  for (long long t = (long long)blockIdx.x * VT + threadIdx.x; t < nown; t += (long long)gridDim.x * VT) {
+    const long long n = L.ob + t;
+    const double r0 = r[n], r1 = r[L.stride + n];
+    z[n] = i00[n] * r0 + i01[n] * r1;
+    z[L.stride + n] = i01[n] * r0 + i11[n] * r1;
+  }
+}
+
+__global__ void __launch_bounds__(VT) k_dot2(VecLayout L, const double* __restrict__ a0, const double* __restrict__ b0,
+                                              const double* __restrict__ a1, const double* __restrict__ b1,
+                                              double* __restrict__ partials) {
+  __shared__ double sm[VT / 32];
+  const Chunk c = my_chunk(L);
+  double s0 = 0.0, s1 = 0.0;
+  for (long long i = c.begin + threadIdx.x; i < c.end; i += VT) {
+    s0 = fma(a0[i], b0[i], s0);
+    if (a1 != nullptr) s1 = fma(a1[i], b1[i], s1);
+  }
+  const double t0 = block_sum(s0, sm);
+  const double t1 = block_sum(s1, sm);
+  if (threadIdx.x == 0) {
+    const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    partials[b * 2] = t0;
+    partials[b * 2 + 1] = t1;
+  }
+}
+
+// p = z + (rz/rz_old) p   with z = dinv.*r (Jacobi), z = r (none) or an explicit z vector
+__global__ void __launch_bounds__(VT) k_cg_p_update(VecLayout L, double* __restrict__ p, const double* __restrict__ r,
+                                                     const double* __restrict__ dinv, const double* __restrict__ z,
+                                                     const double* __restrict__ S) {
+  if (S[S_REASON] != 0.0) return;
+  const double beta = (S[S_ITS] == 0.0) ? 0.0 : S[S_RZ] / S[S_RZ_OLD];
+  const Chunk c = my_chunk(L);
+  long long i = c.begin + threadIdx.x;
+  for (; i + (UNROLL - 1) * VT < c.end; i += UNROLL * VT) {
+    double zv[UNROLL], pv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long q = i + u * VT;
+      zv[u] = z ? z[q] : (dinv ? dinv[q] * r[q] : r[q]);
+      pv[u] = (beta == 0.0) ? 0.0 : p[q];
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) p[i + u * VT] = fma(beta, pv[u], zv[u]);
+  }
+  for (; i < c.end; i += VT) {
+    const double zv = z ? z[i] : (dinv ? dinv[i] * r[i] : r[i]);
+    const double pv = (beta == 0.0) ? 0.0 : p[i];
+    p[i] = fma(beta, pv, zv);
+  }
+}
+
+// x += a p ; r -= a w ; [z = dinv.*r ; partial <r,z>, <z,z>]    a = rz / pAp
+template <bool FUSED_PC>
+__global__ void __launch_bounds__(VT) k_cg_xr_update(VecLayout L, double* __restrict__ x, double* __restrict__ r,
+                                                      const double* __restrict__ p, const double* __restrict__ w,
+                                                      const double* __restrict__ dinv, const double* __restrict__ S,
+                                                      double* __restrict__ partials) {
+  __shared__ double sm[VT / 32];
+  if (S[S_REASON] != 0.0) return;
+  const double a = S[S_RZ] / S[S_PAP];
+  const Chunk c = my_chunk(L);
+  double srz = 0.0, szz = 0.0;
+  long long i = c.begin + threadIdx.x;
+  for (; i + (UNROLL - 1) * VT < c.end; i += UNROLL * VT) {
+    double xv[UNROLL], rv[UNROLL], pv[UNROLL], wv[UNROLL], dv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long q = i + u * VT;
+      xv[u] = x[q]; rv[u] = r[q]; pv[u] = p[q]; wv[u] = w[q];
+      dv[u] = (FUSED_PC && dinv) ? dinv[q] : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long q = i + u * VT;
+      x[q] = fma(a, pv[u], xv[u]);
+      const double rn = fma(-a, wv[u], rv[u]);
+      r[q] = rn;
+      if (FUSED_PC) {
+        const double zv = dv[u] * rn;
+        srz = fma(rn, zv, srz);
+        szz = fma(zv, zv, szz);
+      }
+    }
+  }
+  for (; i < c.end; i += VT) {
+    x[i] = fma(a, p[i], x[i]);
+    const double rn = fma(-a, w[i], r[i]);
+    r[i] = rn;
+    if (FUSED_PC) {
+      const double zv = (dinv ? dinv[i] : 1.0) * rn;
+      srz = fma(rn, zv, srz);
+      szz = fma(zv, zv, szz);
+    }
+  }
+  if (FUSED_PC) {
+    const double t0 = block_sum(srz, sm);
+    const double t1 = block_sum(szz, sm);
+    if (threadIdx.x == 0) {
+      const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      partials[b * 2] = t0;
+      partials[b * 2 + 1] = t1;
+    }
+  }
+}
+
+struct VecPtrs {
+  const double* v[32];
+};
+
+// partials[b*width + j] = <V_j, w> over the block's chunk, j < nv (classical Gram-Schmidt VecMDot)
+__global__ void __launch_bounds__(VT) k_mdot(VecLayout L, VecPtrs V, int nv, const double* __restrict__ w,
+                                              double* __restrict__ partials, int width) {
+  __shared__ double sm[VT / 32];
+  const Chunk c = my_chunk(L);
+  const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+  for (int j0 = 0; j0 < nv; j0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    for (long long i = c.begin + threadIdx.x; i < c.end; i += VT) {
+      const double wv = w[i];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (j0 + q < nv) acc[q] = fma(V.v[j0 + q][i], wv, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (j0 + q < nv) {
+        const double t = block_sum(acc[q], sm);
+        if (threadIdx.x == 0) partials[b * width + j0 + q] = t;
+      }
+    }
+  }
+}
+
+// w -= sum_j h[j] V_j ; partial ||w||^2      (h = S[S_TMP .. S_TMP+nv))
+__global__ void __launch_bounds__(VT) k_maxpy_norm(VecLayout L, VecPtrs V, int nv, double* __restrict__ w,
+                                                    const double* __restrict__ h, double sign,
+                                                    double* __restrict__ partials) {
+  __shared__ double sm[VT / 32];
+  __shared__ double hs[32];
+  if (threadIdx.x < nv) hs[threadIdx.x] = h[threadIdx.x];
+  __syncthreads();
+  const Chunk c = my_chunk(L);
+  double s = 0.0;
+  for (long long i = c.begin + threadIdx.x; i < c.end; i += VT) {
+    double wv = w[i];
+    for (int j = 0; j < nv; ++j) wv = fma(sign * hs[j], V.v[j][i], wv);
+    w[i] = wv;
+    s = fma(wv, wv, s);
+  }
+  if (partials != nullptr) {
+    const double t = block_sum(s, sm);
+    if (threadIdx.x == 0) {
+      const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      partials[b] = t;
+    }
+  }
+}
+
+}  // namespace
+
+int vec_launch_blocks(const dpp_context* ctx, const VecLayout& L) {
+  const long long nown = L.oe - L.ob;
+  long long want = (nown + (long long)VT * UNROLL * 4 - 1) / ((long long)VT * UNROLL * 4);
+  const long long cap = std::max(1, (ctx->sm_count * 8) / std::max(1, L.nf));
+  want = std::max(1LL, std::min(want, cap));
+  return (int)std::min<long long>(want, kMaxPartialBlocks / 2);
+}
+
+#define VLAUNCH(kernel, ...)                                       \
+  do {                                                             \
+    dim3 grid__(vec_launch_blocks(ctx, L), L.nf);                  \
+    kernel<<<grid__, VT, 0, ctx->stream>>>(__VA_ARGS__);           \
+    ctx->launches++;                                               \
+    DPP_CUDA(cudaGetLastError());                                  \
+  } while (0)
+
+int vec_axpby(dpp_context* ctx, const VecLayout& L, double a, const double* x, double b, double* y) {
+  VLAUNCH(k_axpby, L, a, x, b, y);
+  return DPP_OK;
+}
+
+int vec_scale_into(dpp_context* ctx, const VecLayout& L, double a, const double* x, double* y) {
+  VLAUNCH(k_axpby, L, a, x, 0.0, y);
+  return DPP_OK;
+}
+
+int vec_pointwise_mult(dpp_context* ctx, const VecLayout& L, const double* dinv, const double* r, double* z) {
+  VLAUNCH(k_pointwise, L, dinv, r, z);
+  return DPP_OK;
+}
+
+int vec_pbjacobi(dpp_context* ctx, const VecLayout& L, const double* i00, const double* i01, const double* i11,
+                 const double* r, double* z) {
+  dim3 grid(vec_launch_blocks(ctx, L) * 2, 1);
+  k_pbjacobi<<<grid, VT, 0, ctx->stream>>>(L, i00, i01, i11, r, z);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+
+double* hist_device(dpp_context* ctx, int slot) { return ctx->hist_cap[slot] > 0 ? ctx->d_hist[slot] : nullptr; }
+
+int reduce_partials(dpp_context* ctx, int nblocks, int width, int slot, PostOp post, int out_offset) {
+  double* S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
+  const bool dist = ctx->world > 1;
+  k_reduce_partials<<<1, VT, 0, ctx->stream>>>(ctx->d_partials, nblocks, width, S, hist_device(ctx, slot), (int)post,
+                                               dist ? 0 : 1, out_offset);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  if (dist) {
+    DPP_CHECK(comm_allreduce_sum(ctx, S + S_TMP + out_offset, width));
+    if (post != POST_NONE) {
+      k_post_only<<<1, 1, 0, ctx->stream>>>(S, hist_device(ctx, slot), (int)post);
+      ctx->launches++;
+      DPP_CUDA(cudaGetLastError());
+    }
+  }
+  return DPP_OK;
+}
+
+int vec_dot2(dpp_context* ctx, const VecLayout& L, const double* a0, const double* b0, const double* a1,
+             const double* b1, int slot, PostOp post) {
+  dim3 grid(vec_launch_blocks(ctx, L), L.nf);
+  k_dot2<<<grid, VT, 0, ctx->stream>>>(L, a0, b0, a1, b1, ctx->d_partials);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return reduce_partials(ctx, grid.x * grid.y, 2, slot, post);
+}
+
+int cg_p_update(dpp_context* ctx, const VecLayout& L, double* p, const double* r, const double* dinv, const double* z,
+                int slot) {
+  const double* S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
+  VLAUNCH(k_cg_p_update, L, p, r, dinv, z, S);
+  return DPP_OK;
+}
+
+int cg_xr_update(dpp_context* ctx, const VecLayout& L, double* x, double* r, const double* p, const double* w,
+                 const double* dinv, bool fused_pc, int slot, PostOp post) {
+  const double* S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
+  dim3 grid(vec_launch_blocks(ctx, L), L.nf);
+  if (fused_pc) {
+    k_cg_xr_update<true><<<grid, VT, 0, ctx->stream>>>(L, x, r, p, w, dinv, S, ctx->d_partials);
+    ctx->launches++;
+    DPP_CUDA(cudaGetLastError());
+    return reduce_partials(ctx, grid.x * grid.y, 2, slot, post);
+  }
+  k_cg_xr_update<false><<<grid, VT, 0, ctx->stream>>>(L, x, r, p, w, dinv, S, ctx->d_partials);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+
+int gmres_mdot(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, const double* w, int slot) {
+  VecPtrs P{};
+  for (int j = 0; j < nv; ++j) P.v[j] = V[j];
+  dim3 grid(vec_launch_blocks(ctx, L), L.nf);
+  k_mdot<<<grid, VT, 0, ctx->stream>>>(L, P, nv, w, ctx->d_partials, nv);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return reduce_partials(ctx, grid.x * grid.y, nv, slot, POST_NONE);
+}
+
+int gmres_maxpy_norm(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, double* w, int slot) {
+  VecPtrs P{};
+  for (int j = 0; j < nv; ++j) P.v[j] = V[j];
+  const double* S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
+  // h lives in S[S_TMP..]; copy to spare area because the norm reduction overwrites S_TMP
+  double* hcopy = ctx->d_scalars + (size_t)kNumScalars - 40;
+  DPP_CUDA(cudaMemcpyAsync(hcopy, S + S_TMP, sizeof(double) * nv, cudaMemcpyDeviceToDevice, ctx->stream));
+  dim3 grid(vec_launch_blocks(ctx, L), L.nf);
+  k_maxpy_norm<<<grid, VT, 0, ctx->stream>>>(L, P, nv, w, hcopy, -1.0, ctx->d_partials);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  // h stays in S[S_TMP .. S_TMP+nv) for the host; ||w||^2 goes to S[S_TMP + kGmresNormOffset]
+  return reduce_partials(ctx, grid.x * grid.y, 1, slot, POST_NONE, kGmresNormOffset);
+}
+
+int vec_maxpy_host(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, const double* coef,
+                   double* x) {
+  VecPtrs P{};
+  for (int j = 0; j < nv; ++j) P.v[j] = V[j];
+  double* hcopy = ctx->d_scalars + (size_t)kNumScalars - 40;
+  DPP_CUDA(cudaMemcpyAsync(hcopy, coef, sizeof(double) * nv, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid(vec_launch_blocks(ctx, L), L.nf);
+  k_maxpy_norm<<<grid, VT, 0, ctx->stream>>>(L, P, nv, x, hcopy, 1.0, nullptr);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+
+int scalars_fetch(dpp_context* ctx, int slot) {
+  DPP_CUDA(cudaMemcpyAsync(ctx->h_scalars + (size_t)slot * S_SLOT_SIZE, ctx->d_scalars + (size_t)slot * S_SLOT_SIZE,
+                           sizeof(double) * S_SLOT_SIZE, cudaMemcpyDeviceToHost, ctx->stream));
+  DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DPP_OK;
+}
+
+int scalars_init(dpp_context* ctx, int slot, double rtol, double atol, double dtol, int max_it, int hist_cap) {
+  double* h = ctx->h_scalars + (size_t)slot * S_SLOT_SIZE;
+  for (int i = 0; i < S_SLOT_SIZE; ++i) h[i] = 0.0;
+  h[S_RTOL] = rtol; h[S_ATOL] = atol; h[S_DTOL] = dtol; h[S_MAXIT] = (double)max_it;
+  h[S_HISTCAP] = (double)hist_cap; h[S_RZ_OLD] = 1.0;
+  DPP_CUDA(cudaMemcpyAsync(ctx->d_scalars + (size_t)slot * S_SLOT_SIZE, h, sizeof(double) * S_SLOT_SIZE,
+                           cudaMemcpyHostToDevice, ctx->stream));
+  // the pinned mirror is reused by scalars_fetch: make sure the upload has been consumed
+  DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DPP_OK;
+}
+
+int vec_zero(dpp_context* ctx, double* x, int64_t n) {
+  DPP_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, ctx->stream));
+  return DPP_OK;
+}
+
+int vec_copy(dpp_context* ctx, double* dst, const double* src, int64_t n) {
+  DPP_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+  return DPP_OK;
+}
+
+}  // namespace dpp

@@ -1,0 +1,156 @@
+"""Host-side logic that needs no GPU: presets, option translation, mesh/space surface, forms,
+parameter container (mirrors the reference's own CPU-only tests)."""
+import numpy as np
+import pytest
+
+import perphil_b200 as pb
+from perphil_b200 import _lib as L
+from perphil_b200 import parameters as prm
+from oracle import dpp_oracle as orc
+
+
+def test_parameters_defaults():
+    # models/dpp/_tests/test_parameters.py:10-23
+    p = pb.DPPParameters()
+    assert isinstance(p.k1, pb.Constant) and float(p.k1) == 1.0
+    assert float(p.k2) == pytest.approx(1.0 / 1e2)
+    p = pb.DPPParameters(k1=2.0, k2=None, scale_contrast=10.0)
+    assert float(p.k2) == pytest.approx(0.2)
+    p = pb.DPPParameters(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
+    assert p.eta == pytest.approx(np.sqrt(1.01 / 1e-2))
+    assert p.eta == pytest.approx(orc.Params(k2=1e-2).eta)
+
+
+def test_presets_follow_reference_style():
+    # solvers/_tests/test_solver_parameters.py:1-26 style checks on the new presets
+    for name in dir(prm):
+        if name.startswith("B200_") and name.endswith("_PARAMS"):
+            d = getattr(prm, name)
+            assert d[prm.B200_BACKEND_KEY] == prm.B200_BACKEND
+    assert prm.B200_CG_JACOBI_PARAMS["ksp_type"] == "cg" and prm.B200_CG_JACOBI_PARAMS["pc_type"] == "jacobi"
+    assert prm.B200_CG_JACOBI_PARAMS["ksp_rtol"] == 1e-8 and prm.B200_CG_JACOBI_PARAMS["ksp_atol"] == 1e-12
+    assert prm.B200_CG_JACOBI_PARAMS["ksp_max_it"] == 50000
+    assert prm.B200_GMRES_PARAMS["pc_type"] == "none"
+    fs = prm.B200_GMRES_FIELDSPLIT_PARAMS
+    assert fs["pc_type"] == "fieldsplit" and fs["pc_fieldsplit_type"] == "multiplicative"
+    assert fs["pc_fieldsplit_0_fields"] == "0" and fs["pc_fieldsplit_1_fields"] == "1"
+    assert prm.B200_CG_FIELDSPLIT_PARAMS["pc_fieldsplit_type"] == "additive"
+    assert prm.B200_PICARD_SPLIT_PARAMS["snes_rtol"] == 1e-8
+
+
+class _FakeHandle:
+    def default_options(self):
+        import ctypes
+
+        o = L.DppOptions()
+        L.load().dpp_default_options(ctypes.byref(o))
+        return o
+
+
+def test_option_translation():
+    from perphil_b200.solver import options_from_petsc
+
+    h = _FakeHandle()
+    o = options_from_petsc(h, prm.B200_CG_JACOBI_PARAMS)
+    assert (o.ksp_type, o.pc_type, o.operator_mode) == (L.KSP_CG, L.PC_JACOBI, L.OP_MATRIX_FREE)
+    assert (o.rtol, o.atol, o.max_it) == (1e-8, 1e-12, 50000)
+    o = options_from_petsc(h, prm.B200_CG_JACOBI_AIJ_PARAMS)
+    assert o.operator_mode == L.OP_ASSEMBLED
+    o = options_from_petsc(h, prm.B200_GMRES_FIELDSPLIT_PARAMS)
+    assert (o.ksp_type, o.pc_type, o.fieldsplit_type) == (L.KSP_GMRES, L.PC_FIELDSPLIT, L.FS_MULTIPLICATIVE)
+    assert (o.inner_ksp_type, o.inner_pc_type, o.inner_rtol) == (L.INNER_CG, L.PC_JACOBI, 1e-10)
+    o = options_from_petsc(h, prm.B200_PICARD_SPLIT_PARAMS, nonlinear=True)
+    assert o.ksp_type == L.KSP_PICARD and o.rtol == 1e-8
+    # PETSc defaults when keys are absent
+    o = options_from_petsc(h, {"ksp_type": "gmres"})
+    assert (o.rtol, o.atol, o.max_it, o.gmres_restart, o.pc_type) == (1e-5, 1e-50, 10000, 30, L.PC_NONE)
+    # reference presets that need MUMPS/ILU (K8) are refused, not silently replaced
+    with pytest.raises(NotImplementedError):
+        options_from_petsc(h, {"ksp_type": "preonly", "pc_type": "lu"})
+    with pytest.raises(NotImplementedError):
+        options_from_petsc(h, {"ksp_type": "gmres", "pc_type": "ilu"})
+    lu = {"ksp_type": "preonly", "pc_type": "lu"}
+    with pytest.raises(NotImplementedError):
+        options_from_petsc(h, {"ksp_type": "gmres", "pc_type": "fieldsplit", "fieldsplit_0": lu, "fieldsplit_1": lu})
+
+
+@pytest.mark.parametrize("cells,degree", [((4, 5), 1), ((3, 4, 5), 1), ((3, 2), 2), ((2, 3, 2), 2)])
+def test_mesh_matches_oracle_mesh(cells, degree):
+    mesh = pb.UnitSquareMesh(*cells) if len(cells) == 2 else pb.UnitCubeMesh(*cells)
+    _, V = pb.create_function_spaces(mesh, pressure_deg=degree)
+    om = orc.structured_mesh(cells, degree)
+    assert np.array_equal(V.cell_node_map().values, om.cell_node_map)
+    assert np.allclose(V.node_coordinates, om.coords)
+    assert np.array_equal(V.boundary_nodes, om.boundary_nodes)
+    assert np.array_equal(mesh.coordinates.cell_node_map().values, om.cell_vertex_map)
+    assert np.allclose(mesh.coordinates.dat.data_ro, om.vertex_coords)
+    W = V * V
+    assert W.num_sub_spaces() == 2 and W.dim() == 2 * om.n_nodes and W.sub(1).index == 1
+
+
+def test_mesh_contract():
+    # mesh/_tests/test_mesh.py:10-20, forms/_tests/test_spaces.py:11-18
+    mesh = pb.create_mesh(2, 2, quadrilateral=True)
+    assert mesh.geometric_dimension() == 2 and mesh.num_cells() == 4
+    _, V = pb.create_function_spaces(mesh)
+    assert V.dim() == 9
+    with pytest.raises(ValueError):
+        pb.create_mesh(2, 2, quadrilateral=False)
+
+
+def test_forms_structure():
+    # forms/_tests/test_dpp_regressions/test_dpp_form_structure_regression.yml: integrals 4, rank 2
+    mesh = pb.create_mesh(2, 2)
+    _, V = pb.create_function_spaces(mesh)
+    W = V * V
+    p = pb.DPPParameters()
+    a, Lf = pb.dpp_form(W, p)
+    assert len(a.integrals()) == 4 and len(a.arguments()) == 2 and len(Lf.arguments()) == 1
+    with pytest.raises(ValueError):
+        pb.dpp_form(V, p)
+    F, fields = pb.dpp_splitted_form(W, p)
+    assert isinstance(fields, pb.Function) and len(F.arguments()) == 1
+    with pytest.raises(ValueError):
+        pb.dpp_splitted_form(V, p)
+    (a0, L0), (a1, L1) = pb.dpp_delayed_form(V, V, p, pb.Function(V), pb.Function(V))
+    assert a0.blocks == ((0, 0),) and a1.blocks == ((1, 1),)
+    assert [i.coefficient for i in a1.integrals()] == [1e-2, 1.0]
+
+
+def test_manufactured_matches_oracle():
+    p = pb.DPPParameters(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
+    for cells in [(4, 4), (3, 3, 3)]:
+        mesh = pb.UnitSquareMesh(*cells) if len(cells) == 2 else pb.UnitCubeMesh(*cells)
+        _, V = pb.create_function_spaces(mesh)
+        _, e1, _, e2 = pb.exact_expressions(mesh, p)
+        o1, o2 = orc.exact_pressures(V.node_coordinates, orc.Params(k2=1e-2))
+        assert np.array_equal(e1(V.node_coordinates), o1) and np.array_equal(e2(V.node_coordinates), o2)
+
+
+def test_bc_data_extraction():
+    from perphil_b200.provider import bc_data, space_data
+
+    mesh = pb.UnitCubeMesh(3, 3, 3)
+    _, V = pb.create_function_spaces(mesh)
+    W = V * V
+    bcs = [pb.DirichletBC(W.sub(0), pb.Constant(1.0), "on_boundary"), pb.DirichletBC(W.sub(1), lambda X: X[:, 0], "on_boundary")]
+    out = bc_data(W, bcs)
+    assert [f for f, _, _ in out] == [0, 1]
+    assert np.all(out[0][2] == 1.0) and np.allclose(out[1][2], V.node_coordinates[V.boundary_nodes, 0])
+    sd = space_data(W)
+    assert (sd.dim, sd.degree, sd.n_nodes) == (3, 1, 64)
+
+
+def test_local_order_normalisation():
+    from perphil_b200.provider import normalise_local_order
+
+    om = orc.structured_mesh((3, 2, 2), 1)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(8)
+    scrambled = om.cell_node_map[:, perm]
+    assert np.array_equal(normalise_local_order(scrambled, om.coords), om.cell_node_map)
+    # per-cell different orders
+    s2 = om.cell_node_map.copy()
+    for c in range(s2.shape[0]):
+        s2[c] = s2[c, rng.permutation(8)]
+    assert np.array_equal(normalise_local_order(s2, om.coords), om.cell_node_map)
