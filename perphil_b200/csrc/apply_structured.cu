@@ -80,10 +80,13 @@ __global__ void __launch_bounds__(TKW* TJ) k_apply_q1(const StructArgs s) {
   }
 
   double qc[NF][3], qd[NF][3];
+  double xcen[NF][2];  // this thread's (masked) input value at planes i-1, i
 #pragma unroll
-  for (int f = 0; f < NF; ++f)
+  for (int f = 0; f < NF; ++f) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) qc[f][d] = qd[f][d] = 0.0;
+    xcen[f][0] = xcen[f][1] = 0.0;
+  }
 
   double dot = 0.0;
   const int tile_elems = (TJ + 2) * (TKW + 2);
@@ -116,7 +119,10 @@ __global__ void __launch_bounds__(TKW* TJ) k_apply_q1(const StructArgs s) {
       qd[f][0] = qd[f][1];
       qd[f][1] = qd[f][2];
       double c = 0.0, d = 0.0;
+      xcen[f][0] = xcen[f][1];
+      xcen[f][1] = 0.0;
       if (in_dom && active) {
+        xcen[f][1] = xs[b][f][ty + 1][tx + 1];
 #pragma unroll
         for (int dj = 0; dj < 3; ++dj)
 #pragma unroll
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(TKW* TJ) k_apply_q1(const StructArgs s) {
           xc = s.x[f][node];
           yv = s.identity_on_masked ? xc : 0.0;
         } else {
-          xc = xs[b ^ 1][f][ty + 1][tx + 1];
+          xc = xcen[f][0];  // (the other smem buffer may already be refilled by a faster warp)
         }
         s.y[f][node] = yv;
         dot = fma(xc, yv, dot);
@@ -360,6 +366,13 @@ int structured_detect_and_setup(dpp_context* ctx, const int32_t* cnm, const doub
     std::memcpy(&host[off], k.data(), k.size() * sizeof(double));
     off += k.size();
     ctx->h_axis[a] = ax[a];
+    if (a == 0) {  // centre entries of axis 0: [interior, domain boundary] (uniform kernel)
+      const int n0 = nn[0], w0 = 2 * p + 1;
+      ctx->uni_mxc[1] = m[p];
+      ctx->uni_kxc[1] = k[p];
+      ctx->uni_mxc[0] = n0 > 2 ? m[(size_t)w0 + p] : m[p];
+      ctx->uni_kxc[0] = n0 > 2 ? k[(size_t)w0 + p] : k[p];
+    }
   }
   DPP_CHECK(dev_alloc(ctx, &ctx->d_tables, (int64_t)total));
   DPP_CUDA(cudaMemcpy(ctx->d_tables, host.data(), total * sizeof(double), cudaMemcpyHostToDevice));
@@ -370,6 +383,19 @@ int structured_detect_and_setup(dpp_context* ctx, const int32_t* cnm, const doub
   }
   ctx->grid.band = p;
   ctx->structured_ok = true;
+  // uniform spacing per axis?  (then all off-diagonals of the 1-D matrices coincide)
+  bool uni = (p == 1);
+  for (int a = 0; a < 3 && uni; ++a) {
+    const std::vector<double>& v = ax[a];
+    if (v.size() < 2) { ctx->uni_m_off[a] = ctx->uni_k_off[a] = 0.0; continue; }
+    const double h0 = v[1] - v[0];
+    for (size_t t = 2; t < v.size(); ++t)
+      if (std::fabs((v[t] - v[t - 1]) - h0) > 1e-12 * std::fabs(h0)) uni = false;
+    ctx->uni_m_off[a] = h0 / 6.0;
+    ctx->uni_k_off[a] = -1.0 / h0;
+  }
+  ctx->grid_uniform = uni;
+  if (const char* e = getenv("DPP_FORCE_TABLE_KERNEL")) ctx->force_table_kernel = (e[0] == '1');
   return DPP_OK;
 }
 
@@ -378,6 +404,7 @@ int structured_apply_q2(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks
 int structured_apply(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks) {
   const GridDesc& g = ctx->grid;
   if (g.band == 2) return structured_apply_q2(ctx, a, n_partial_blocks);
+  if (ctx->grid_uniform && !ctx->force_table_kernel) return structured_apply_uniform(ctx, a, n_partial_blocks);
   const long long plane = (long long)g.n[1] * g.n[2];
   if (a.owned_begin % plane || a.owned_end % plane) {
     ctx->set_error("structured apply: owned range must consist of whole x-planes");

@@ -48,6 +48,7 @@ struct OpArgs {
   double* dot_partials;        // optional: per-block partial sums of sum_f <x_f, y_f> over owned rows
   int64_t owned_begin, owned_end;  // rows (local node ids) to compute
   const double* skip_flag;     // optional device scalar: != 0 -> the launch is a no-op
+  int input_premasked;         // caller guarantees x == 0 wherever in_mask != 0 (all Krylov vectors)
 };
 
 // Tensor-grid description for the structured family. Axis 0 = x (slowest), 2 = z (contiguous).
@@ -88,6 +89,10 @@ struct dpp_context {
   dpp::GridDesc grid{};
   double* d_tables = nullptr;     // backing store of grid.m1d/k1d
   std::vector<double> h_axis[3];  // 1-D vertex coordinates per axis (structured)
+  bool grid_uniform = false;      // equal spacing on every axis -> apply_structured_uniform.cu
+  bool force_table_kernel = false;
+  double uni_m_off[3] = {0, 0, 0}, uni_k_off[3] = {0, 0, 0};
+  double uni_mxc[2] = {0, 0}, uni_kxc[2] = {0, 0};  // axis-0 centre entries [interior, boundary]
 
   // general family: node -> (cell, local index) adjacency, per-cell geometry
   int64_t* d_adj_ptr = nullptr;   // [n_nodes+1]
@@ -105,6 +110,8 @@ struct dpp_context {
   uint8_t* d_mask = nullptr;      // [2*n_nodes]
   double* d_g = nullptr;          // [2*n_nodes]  (0 where unconstrained)
   bool have_bc[2] = {false, false};
+  int32_t* d_bc_nodes[2] = {nullptr, nullptr};  // constrained node ids per field
+  int64_t n_bc[2] = {0, 0};
 
   // partition
   int rank = 0, world = 1;
@@ -116,6 +123,7 @@ struct dpp_context {
   dpp::CsrMatrix* csr = nullptr;
   double* d_solution = nullptr;   // [2*n_nodes]
   double* d_diag = nullptr;       // [2*n_nodes] diag(A_bc), valid when diag_valid
+  double* d_premask = nullptr;    // [2*n_nodes] scratch: input with eliminated columns zeroed
   bool diag_valid = false;
 
   // reduction scratch
@@ -140,6 +148,7 @@ int structured_detect_and_setup(dpp_context* ctx, const int32_t* cnm_host, const
                                 const int32_t* ccnm_host);
 int structured_apply(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks);
 int structured_diagonal(dpp_context* ctx, const Coef& c, double* d_diag /*[2*n_nodes]*/);
+int structured_apply_uniform(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks);
 
 // ---- apply_general.cu
 int general_setup(dpp_context* ctx, const int32_t* cnm_host);

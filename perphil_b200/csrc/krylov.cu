@@ -96,6 +96,7 @@ int apply_spec(dpp_context* ctx, const OpSpec& op, const double* x, double* y, b
   a.owned_end = ctx->owned_end;
   a.dot_partials = want_dot ? ctx->d_partials : nullptr;
   a.skip_flag = skip;
+  a.input_premasked = 1;  // Krylov vectors are exactly zero on eliminated rows/columns
   if (op.nf == 2) {
     a.c = dpp_coef(ctx);
     for (int f = 0; f < 2; ++f) {
