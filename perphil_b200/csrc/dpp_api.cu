@@ -183,7 +183,7 @@ int dpp_set_params(dpp_handle ctx, double k1, double k2, double beta, double mu)
   ctx->k1 = k1; ctx->k2 = k2; ctx->beta = beta; ctx->mu = mu;
   ctx->have_params = true;
   ctx->invalidate();
-  dpp::csr_destroy(ctx);
+  dpp::csr_invalidate(ctx);
   return DPP_OK;
 }
 
@@ -223,7 +223,7 @@ int dpp_set_dirichlet(dpp_handle ctx, int field, int64_t n, const int32_t* nodes
   ctx->n_bc[field] = n;
   ctx->have_bc[field] = n > 0;
   ctx->invalidate();
-  dpp::csr_destroy(ctx);
+  dpp::csr_invalidate(ctx);
   return DPP_OK;
 }
 
@@ -235,11 +235,11 @@ static int apply_common(dpp_context* ctx, const double* x, double* y, int mode, 
   }
   const int64_t n = ctx->n_nodes;
   if (mode == DPP_OP_ASSEMBLED) {
-    if (!ctx->csr) {
+    if (!dpp::csr_valid(ctx)) {
       int64_t nnz = 0;
       DPP_CHECK(dpp::csr_assemble(ctx, &nnz));
     }
-    return dpp::csr_spmv(ctx, x, y, want_dot ? ctx->d_partials : nullptr, nb);
+    return dpp::csr_spmv(ctx, x, y, want_dot ? ctx->d_partials : nullptr, nb, nullptr);
   }
   dpp::OpArgs a{};
   a.nf = 2;

@@ -173,7 +173,10 @@ void comm_destroy(dpp_context* ctx);
 // ---- assemble_csr.cu
 int csr_assemble(dpp_context* ctx, int64_t* nnz);
 int csr_export(dpp_context* ctx, int64_t* indptr, int32_t* indices, double* data);
-int csr_spmv(dpp_context* ctx, const double* x, double* y, double* dot_partials, int* n_partial_blocks);
+int csr_spmv(dpp_context* ctx, const double* x, double* y, double* dot_partials, int* n_partial_blocks,
+             const double* skip_flag);
+void csr_invalidate(dpp_context* ctx);
+bool csr_valid(const dpp_context* ctx);
 void csr_destroy(dpp_context* ctx);
 
 // ---- krylov.cu

@@ -87,7 +87,7 @@ int apply_spec(dpp_context* ctx, const OpSpec& op, const double* x, double* y, b
       return DPP_ERR_INVALID;
     }
     ctx->krylov->apply_count++;
-    return csr_spmv(ctx, x, y, want_dot ? ctx->d_partials : nullptr, nblocks);
+    return csr_spmv(ctx, x, y, want_dot ? ctx->d_partials : nullptr, nblocks, skip);
   }
   OpArgs a{};
   a.nf = op.nf;
@@ -504,7 +504,7 @@ int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_r
   const VecLayout L2 = layout(ctx, 2);
   K->inner_its = 0;
   K->apply_count = 0;
-  if (opt->operator_mode == DPP_OP_ASSEMBLED && ctx->csr == nullptr) {
+  if (opt->operator_mode == DPP_OP_ASSEMBLED && !csr_valid(ctx)) {
     int64_t nnz = 0;
     DPP_CHECK(csr_assemble(ctx, &nnz));
   }

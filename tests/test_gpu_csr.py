@@ -1,0 +1,150 @@
+"""GPU assembly parity (K1/K2/K3a): CSR sparsity and DOF indexing bit-exact, assembled values within
+1e-12 relative (north_star), through perphil's own assembled-matrix boundary
+`get_matrix_data_from_form(a, bcs)` (solvers/conditioning.py:66-102)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import perphil_b200 as pb
+from perphil_b200 import _lib as L
+from oracle import dpp_oracle as orc
+from tests.util import configured_handle, make_problem, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _full_pattern_reference(osys):
+    """Oracle matrix with BCs applied but explicit zeros KEPT on the full element pattern."""
+    A = osys.A.tocsr().copy()
+    A.sort_indices()
+    keep = osys.interior
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    data = A.data * keep[rows] * keep[A.indices]
+    diag = (rows == A.indices) & (keep[rows] == 0)
+    data[diag] = 1.0
+    return A.indptr.astype(np.int64), A.indices.astype(np.int32), data
+
+
+@pytest.mark.parametrize("cells,degree", [((8, 8, 8), 1), ((5, 7, 9), 1), ((16, 16), 1), ((10, 10), 1),
+                                          ((3, 4, 5), 2), ((6, 5), 2)])
+@pytest.mark.parametrize("bc", ["manufactured", "none"])
+def test_csr_pattern_bit_exact_and_values(cells, degree, bc):
+    W, p, bcs, osys = make_problem(cells, degree, bc=bc)
+    h = configured_handle(W, p, bcs)
+    indptr, indices, data = h.assemble_csr()
+    rp, ri, rd = _full_pattern_reference(osys)
+    assert indptr.dtype == np.int64 and indices.dtype == np.int32
+    assert np.array_equal(indptr, rp)
+    assert np.array_equal(indices, ri)
+    scale = np.abs(rd).max()
+    assert np.abs(data - rd).max() <= 1e-12 * scale
+    # exact structure of the Dirichlet rows/columns: exact zeros and exact ones
+    assert np.array_equal(data == 0.0, rd == 0.0) or bc == "none"
+
+
+def test_public_matrix_data_matches_reference_counts():
+    """3-D N=8 -> 62 500 full / 28 208 after eliminate_zeros; 2-D N=16 -> 9 604 / 7 524."""
+    for cells, full, elim in [((8, 8, 8), 62500, 28208), ((16, 16), 9604, 7524)]:
+        W, p, bcs, osys = make_problem(cells, 1)
+        a, _ = pb.dpp_form(W, p)
+        raw = pb.assemble_bilinear_form(a, bcs)
+        assert raw[1].size == full
+        md = pb.get_matrix_data_from_form(a, bcs)
+        assert isinstance(md, pb.MatrixData)
+        assert md.number_of_dofs == W.dim() == osys.n_dof
+        assert md.number_of_nonzero_entries == md.sparse_csr_data.nnz == elim == osys.A_bc.nnz
+        assert md.is_symmetric
+        ref = osys.A_bc
+        assert np.array_equal(md.sparse_csr_data.indptr, ref.indptr)
+        assert np.array_equal(md.sparse_csr_data.indices, ref.indices)
+        assert np.abs(md.sparse_csr_data.data - ref.data).max() <= 1e-12 * np.abs(ref.data).max()
+        # block layout [p1; p2] (iterative_bench.py:323-324)
+        n = W.sub(0).dim()
+        A00 = md.sparse_csr_data[:n, :n]
+        assert abs(A00 - ref[:n, :n]).max() <= 1e-12 * np.abs(ref.data).max()
+
+
+def test_conditioning_from_gpu_matrix(golden):
+    """conditioning_3d.csv through the GPU-assembled matrix (N=4: kappa = 166.5757...)."""
+    row = golden["conditioning_3d_hex_q1"][0]
+    W, p, bcs, _ = make_problem((row["N"],) * 3, 1)
+    a, _ = pb.dpp_form(W, p)
+    md = pb.get_matrix_data_from_form(a, bcs)
+    n = row["n0"]
+    assert orc.condition_number_dense(md.sparse_csr_data) == pytest.approx(row["cond_monolithic"], rel=1e-10)
+    assert orc.condition_number_dense(md.sparse_csr_data[:n, :n]) == pytest.approx(row["cond_macro"], rel=1e-10)
+    assert orc.condition_number_dense(md.sparse_csr_data[n:, n:]) == pytest.approx(row["cond_micro"], rel=1e-10)
+
+
+def test_csr_on_unstructured_numbering():
+    from tests.test_gpu_parity import _shuffled_distorted
+    from perphil_b200.backend import DppHandle
+
+    for degree, distort in [(1, 0.0), (1, 0.3), (2, 0.25)]:
+        m2 = _shuffled_distorted((4, 5, 3), degree, distort, seed=4)
+        prm = orc.Params(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
+        rng = np.random.default_rng(9)
+        nb = m2.boundary_nodes
+        g1, g2 = rng.standard_normal(nb.size), rng.standard_normal(nb.size)
+        osys = orc.build_system(m2, prm, (nb, g1, nb, g2))
+        h = DppHandle(m2.dim, degree, m2.cell_node_map, m2.vertex_coords, m2.cell_vertex_map, n_nodes=m2.n_nodes)
+        h.set_params(prm.k1, prm.k2, prm.beta, prm.mu)
+        h.set_dirichlet(0, nb, g1); h.set_dirichlet(1, nb, g2)
+        indptr, indices, data = h.assemble_csr()
+        rp, ri, rd = _full_pattern_reference(osys)
+        assert np.array_equal(indptr, rp) and np.array_equal(indices, ri)
+        assert np.abs(data - rd).max() <= 1e-12 * np.abs(rd).max()
+        x = rng.standard_normal(osys.n_dof)
+        assert rel_err(h.apply(x, assembled=True), osys.A_bc @ x) < 1e-13
+        h.close()
+
+
+@pytest.mark.parametrize("cells", [(8, 8, 8), (16, 16)])
+def test_spmv_and_assembled_solve(cells):
+    W, p, bcs, osys = make_problem(cells, 1)
+    h = configured_handle(W, p, bcs)
+    x = np.random.default_rng(0).standard_normal(osys.n_dof)
+    y_csr = h.apply(x, assembled=True)
+    assert rel_err(y_csr, osys.A_bc @ x) < 1e-13
+    assert rel_err(y_csr, h.apply(x)) < 1e-13          # assembled == matrix-free
+    ref = orc.solve_dpp_oracle(osys, "cg", "jacobi")
+    sol = pb.solve_dpp(W, p, bcs, solver_parameters=pb.B200_CG_JACOBI_AIJ_PARAMS)
+    assert sol.iteration_number == ref.iteration_number
+    u = np.concatenate([sol.solution.sub(0).dat.data, sol.solution.sub(1).dat.data])
+    assert rel_err(u, ref.u) < 1e-9
+
+
+def test_reassembly_after_parameter_change_keeps_pattern():
+    W, p, bcs, _ = make_problem((6, 6, 6), 1)
+    h = configured_handle(W, p, bcs)
+    ip0, ix0, d0 = h.assemble_csr()
+    h.set_params(2.0, 3e-3, 5.0, 0.5)
+    ip1, ix1, d1 = h.assemble_csr()
+    assert np.array_equal(ip0, ip1) and np.array_equal(ix0, ix1) and not np.array_equal(d0, d1)
+    osys = orc.build_system(orc.structured_mesh((6, 6, 6), 1), orc.Params(k1=2.0, k2=3e-3, beta=5.0, mu=0.5), "manufactured")
+    _, _, rd = _full_pattern_reference(osys)
+    assert np.abs(d1 - rd).max() <= 1e-12 * np.abs(rd).max()
+    # bitwise repeatable (no atomics anywhere)
+    _, _, d2 = h.assemble_csr()
+    assert np.array_equal(d1, d2)
+
+
+def test_assembly_128_properties():
+    """BASELINE config 2 top size: nnz = 4 (3N+1)^3 = 228 266 500, row sums of the un-constrained
+    matrix vanish (K 1 = 0, mass blocks cancel), SpMV == matrix-free apply."""
+    N = 128
+    mesh = pb.UnitCubeMesh(N, N, N)
+    _, V = pb.create_function_spaces(mesh)
+    W = V * V
+    prm = pb.DPPParameters(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
+    h = configured_handle(W, prm, [])
+    import ctypes as C
+
+    nnz = C.c_int64()
+    assert h._lib.dpp_assemble_csr(h._h, C.byref(nnz)) == 0
+    assert nnz.value == 4 * (3 * N + 1) ** 3 == 228266500
+    n = h.n_nodes
+    ones = np.ones(2 * n)
+    assert np.abs(h.apply(ones, assembled=True)).max() < 1e-12
+    x = np.random.default_rng(0).standard_normal(2 * n)
+    assert rel_err(h.apply(x, assembled=True), h.apply(x)) < 1e-13
