@@ -563,6 +563,7 @@ int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_r
   if (!ctx->d_solution) DPP_CHECK(dev_alloc(ctx, &ctx->d_solution, 2 * n));
   DPP_CHECK(vec_copy(ctx, ctx->d_solution, ctx->d_g, 2 * n));
   DPP_CHECK(vec_axpby(ctx, L2, 1.0, K->x, 1.0, ctx->d_solution));
+  DPP_CHECK(halo(ctx, ctx->d_solution, 2));  // ghost planes of the returned vector are consistent
   if (u_host) {
     DPP_CUDA(cudaMemcpyAsync(u_host, ctx->d_solution, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
   }
