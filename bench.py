@@ -243,7 +243,7 @@ def main():
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_apply_q1<2> (matrix-free apply + fused <p,Ap>)" if structured else "k_general",
+        "roofline": {"bound": "hbm", "kernel": "k_apply_uniform<2> + k_fix_rows (matrix-free apply, fused <p,Ap>)" if structured else "k_general",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_kind": peak_kind, "bytes_model": "34 B/node structured" if structured else "58 B/node + 32 B/cell",
                      "algorithmic_bytes": alg_bytes},

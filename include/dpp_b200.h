@@ -166,6 +166,10 @@ int dpp_solve(dpp_handle h, const dpp_options* opt, double* u_host, dpp_result* 
               double* residual_history_host, int32_t history_capacity);
 const double* dpp_solution_dev(dpp_handle h);
 
+/* ---- page-locked host buffers for results (full-rate D2H of the solution vector) -------------- */
+int dpp_host_alloc(void** ptr, int64_t bytes);   /* cudaMallocHost */
+int dpp_host_free(void* ptr);
+
 /* ---- measurement helpers (bench.py; timed with CUDA events on the handle's stream) ----------- */
 
 /* mean device milliseconds of `reps` back-to-back applies of the monolithic operator on internal

@@ -374,6 +374,13 @@ int dpp_time_apply(dpp_handle ctx, int mode, int warmup, int reps, int with_dot,
   return DPP_OK;
 }
 
+int dpp_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return DPP_ERR_INVALID;
+  return cudaMallocHost(ptr, (size_t)bytes) == cudaSuccess ? DPP_OK : DPP_ERR_CUDA;
+}
+
+int dpp_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? DPP_OK : DPP_ERR_CUDA; }
+
 int dpp_kernel_launch_count(dpp_handle ctx, int64_t* launches) {
   if (!ctx || !launches) return DPP_ERR_INVALID;
   *launches = ctx->launches;

@@ -195,15 +195,22 @@ class MixedFunctionSpace:
 class Function:
     """Nodal coefficient vector(s) on a (mixed) space; `.dat.data` like Firedrake."""
 
-    def __init__(self, space, name: Optional[str] = None, val=None):
+    def __init__(self, space, name: Optional[str] = None, val=None, buffer: Optional[np.ndarray] = None):
         self._space = space
         self.name = name
         if isinstance(space, MixedFunctionSpace):
-            self._subs = tuple(Function(space.sub(i)) for i in range(space.num_sub_spaces()))
+            # one contiguous field-blocked vector [p1; p2]; the sub-functions are views into it
+            dims = [space.sub(i).dim() for i in range(space.num_sub_spaces())]
+            flat = np.zeros(sum(dims)) if buffer is None else buffer
+            offs = np.concatenate([[0], np.cumsum(dims)])
+            self.vector = flat
+            self._subs = tuple(Function(space.sub(i), val=flat[offs[i]: offs[i + 1]])
+                               for i in range(space.num_sub_spaces()))
             self.dat = _Dat([f.dat.data for f in self._subs])
         else:
             self._subs = ()
             self.dat = _Dat(np.zeros(space.dim()) if val is None else np.asarray(val, dtype=float))
+            self.vector = self.dat.data
 
     def function_space(self):
         return self._space
@@ -254,12 +261,16 @@ class DirichletBC:
         self.function_arg = g
         self.sub_domain = sub_domain
         self.nodes = V.boundary_nodes
+        # like Firedrake, the boundary expression is interpolated when the BC is built
+        self._values = np.ascontiguousarray(evaluate(g, V.node_coordinates[self.nodes]), dtype=np.float64)
+        if isinstance(g, Function):
+            self._values = np.ascontiguousarray(g.dat.data[self.nodes])
 
     def function_space(self):
         return self._V
 
     def values(self) -> np.ndarray:
-        return evaluate(self.function_arg, self._V.node_coordinates[self.nodes])
+        return self._values
 
 
 def UnitSquareMesh(nx: int, ny: int, quadrilateral: bool = True, comm=None) -> Mesh:

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from . import _lib as L
-from .backend import DppHandle
+from .backend import PINNED, DppHandle
 from .forms import dpp_form, dpp_splitted_form
 from .mesh import Function, MixedFunctionSpace
 from .parameters import B200_BACKEND, B200_BACKEND_KEY, DPPParameters
@@ -167,11 +167,16 @@ def _run(W, model_params, bcs, params, nonlinear, fields=None, monitor=None):
         h.set_dirichlet(f, n, v)
     opt = options_from_petsc(h, params, nonlinear)
     hist_cap = int(params.get("b200_history", 0)) or (min(opt.max_it + 1, 1 << 16) if "ksp_monitor" in params else 0)
-    u, info = h.solve(opt, want_solution=True, history=hist_cap)
-    sol = fields if fields is not None else _new_function(W)
     n = h.n_nodes
-    sol.sub(0).dat.data[:] = u[:n]
-    sol.sub(1).dat.data[:] = u[n:]
+    if fields is None and isinstance(W, MixedFunctionSpace):
+        # the result Function is backed by a page-locked buffer: D2H lands in it directly
+        sol = Function(W, buffer=PINNED.take(2 * n))
+        _, info = h.solve(opt, want_solution=True, history=hist_cap, out=sol.vector)
+    else:
+        u, info = h.solve(opt, want_solution=True, history=hist_cap)
+        sol = fields if fields is not None else _new_function(W)
+        sol.sub(0).dat.data[:] = u[:n]
+        sol.sub(1).dat.data[:] = u[n:]
     if "ksp_monitor" in params or "snes_monitor" in params:
         tag = "SNES Function norm" if nonlinear else "KSP Residual norm"
         for i, r in enumerate(info.history):
