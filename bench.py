@@ -23,6 +23,11 @@ if ROOT not in sys.path:
 import numpy as np
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+# (profiles/): filled in after each profiling pass, None until a capture of the current kernel exists.
+TRAFFIC_NCU = {"fused_apply": None}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -86,50 +91,57 @@ def build_problem(N, comm=None):
 
 
 def cpu_baseline(N, repeats=1):
-    """Oracle (numpy/scipy port of the PETSc path) Jacobi-CG on a bounded sample of the workload."""
-    from oracle import dpp_oracle as orc
+    """C/OpenMP restatement of the reference's CPU path (assembled AIJ + SeqAIJ MatMult + KSPCG/PCJACOBI,
+    oracle/dpp_oracle_c.c) on a bounded sample of the workload, all host threads."""
+    from oracle import c_oracle as co
 
     t0 = time.perf_counter()
-    osys = orc.build_system(orc.structured_mesh((N, N, N), 1), orc.Params(k1=1.0, k2=1e-2, beta=1.0, mu=1.0),
-                            "manufactured", route="kron")
+    csys = co.manufactured_system((N, N, N), 1)
     t_asm = time.perf_counter() - t0
-    best = None
+    best, res = None, None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        sol = orc.solve_dpp_oracle(osys, "cg", "jacobi")
+        res = csys.cg("jacobi", want_solution=False)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    ndof = osys.n_dof
-    return {"value": ndof * sol.iteration_number / best / 1e9, "unit": "GDoF/s", "cores": 1, "kind": "port",
-            "sample": f"{N}^3 hex Q1 ({ndof} DoF), scipy CSR SpMV + numpy BLAS-1 Jacobi-CG, {sol.iteration_number} its "
-                      f"in {best:.2f} s (assembly {t_asm:.1f} s not included)",
-            "iterations": int(sol.iteration_number), "seconds": best}
+    ndof, nnz = csys.n_dof, csys.nnz
+    csys.close()
+    return {"value": ndof * res.iteration_number / best / 1e9, "unit": "GDoF/s", "cores": co.num_threads(),
+            "kind": "port",
+            "sample": f"{N}^3 hex Q1 ({ndof} DoF, nnz {nnz}), C/OpenMP CSR SpMV + Jacobi-CG (PETSc KSPCG semantics), "
+                      f"{res.iteration_number} its in {best:.2f} s (assembly {t_asm:.1f} s not included; "
+                      f"SpMV {100 * res.spmv_seconds / best:.0f}% of the solve)",
+            "iterations": int(res.iteration_number), "seconds": best, "host_cpus": os.cpu_count()}
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement of the PETSc path, timed on the host cores."""
+    """--impl reference: the reference's CPU path for this metric.  perphil itself is Python glue over
+    Firedrake/PETSc, which cannot be installed here or on the GPU box, so the arm times the
+    C/OpenMP restatement of that path (oracle/dpp_oracle_c.c) with all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import dpp_oracle as orc
+    from oracle import c_oracle as co
 
     N = args.ref_size
-    osys = orc.build_system(orc.structured_mesh((N, N, N), 1), orc.Params(k1=1.0, k2=1e-2, beta=1.0, mu=1.0),
-                            "manufactured", route="kron")
+    csys = co.manufactured_system((N, N, N), 1)
+    res = None
     for _ in range(args.warmup):
-        sol = orc.solve_dpp_oracle(osys, "cg", "jacobi")
+        res = csys.cg("jacobi", want_solution=False)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        sol = orc.solve_dpp_oracle(osys, "cg", "jacobi")
+        res = csys.cg("jacobi", want_solution=False)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    val = osys.n_dof * sol.iteration_number / dt / 1e9
+    val = csys.n_dof * res.iteration_number / dt / 1e9
+    sample = (f"{N}^3 hex Q1 ({csys.n_dof} DoF), assembled CSR SpMV + Jacobi-CG, {res.iteration_number} its per step, "
+              f"{co.num_threads()} OpenMP threads")
     line = {
         "impl": "reference", "metric": "dpp_solve_gdofs", "value": val, "unit": "GDoF/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"3D hex Q1 {args.size}^3 monolithic DPP Jacobi-CG rtol 1e-8 (bounded sample {N}^3)"},
-        "cpu_baseline": {"value": val, "unit": "GDoF/s", "cores": 1, "kind": "port",
-                         "sample": f"{N}^3 hex Q1, {sol.iteration_number} its per step"},
+        "iterations": int(res.iteration_number),
+        "cpu_baseline": {"value": val, "unit": "GDoF/s", "cores": co.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -142,8 +154,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--size", type=int, default=256, help="cells per direction (BASELINE configs[2]: 256)")
-    ap.add_argument("--ref-size", type=int, default=64)
-    ap.add_argument("--cpu-size", type=int, default=64)
+    ap.add_argument("--ref-size", type=int, default=96)
+    ap.add_argument("--cpu-size", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -215,15 +227,34 @@ def main():
     h2d = 2 * nb * (4 + 8) * world if comm is None else comm.sum_int(2 * nb * (4 + 8))
     d2h = 2 * info.n_nodes * 8 if comm is None else comm.sum_int(2 * info.n_nodes * 8)
 
-    # ---- apply roofline (dominant operator kernel), CUDA events inside the library
-    apply_ms = h.time_apply(reps=20, warmup=3, with_dot=True)
-    if comm is not None:
-        apply_ms = comm.max_float(apply_ms)
+    # ---- roofline of the dominant kernel, CUDA events on the library's stream (each kernel timed alone)
+    apply_ms = h.time_apply(reps=20, warmup=3, with_dot=True)      # plain matrix-free apply (MatMult)
     peak, peak_kind = measured_peaks()
     structured = info.kernel_family == 1
-    alg_bytes = 34 * n_nodes_global if structured else 58 * n_nodes_global + 32 * N ** 3
-    achieved = alg_bytes / (apply_ms * 1e-3) / 1e9 / world
-    iter_bytes = alg_bytes + 88 * ndof          # fused Jacobi-PCG minimum
+    apply_bytes = 34 * n_nodes_global if structured else 58 * n_nodes_global + 32 * N ** 3
+    fused = structured
+    try:
+        fa_ms, fu_ms = h.time_cg_kernels(reps=20, warmup=3)
+    except Exception:
+        fused, fa_ms, fu_ms = False, None, None
+    if comm is not None:
+        apply_ms = comm.max_float(apply_ms)
+        if fused:
+            fa_ms, fu_ms = comm.max_float(fa_ms), comm.max_float(fu_ms)
+    if fused:
+        # k_cg_fused_apply: reads r, p_old, x and writes p, A p, x (6 passes of 8 B per DoF) + the 1 B/DoF
+        # Dirichlet information (row fix-up list); k_cg_r_update: reads r, A p, writes r (3 passes)
+        dom_name = "k_cg_fused_apply<2> (+k_fix_rows): p/x update + matrix-free apply + <p,Ap>"
+        dom_bytes = (6 * 8 + 1) * ndof
+        dom_ms = fa_ms
+        iter_bytes = dom_bytes + 3 * 8 * ndof
+        bytes_model = "49 B/DoF: r, p_old, x in; p, Ap, x out; 1 B/DoF Dirichlet rows"
+    else:
+        dom_name = "k_apply (matrix-free apply, fused <p,Ap>)"
+        dom_bytes, dom_ms = apply_bytes, apply_ms
+        iter_bytes = apply_bytes + 88 * ndof      # unfused-kernel minimum
+        bytes_model = "58 B/node + 32 B/cell"
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 / world
     solve_gbs = iter_bytes * its / (np.mean([m for m in dev_ms]) * 1e-3) / 1e9 / world
 
     if rank != 0:
@@ -243,10 +274,14 @@ def main():
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_apply_uniform<2> + k_fix_rows (matrix-free apply, fused <p,Ap>)" if structured else "k_general",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_kind": peak_kind, "bytes_model": "34 B/node structured" if structured else "58 B/node + 32 B/cell",
-                     "algorithmic_bytes": alg_bytes},
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": TRAFFIC_NCU.get("fused_apply") if fused else None,
+                     "peak_kind": peak_kind, "bytes_model": bytes_model, "algorithmic_bytes": dom_bytes,
+                     "ms_per_launch": dom_ms},
+        "kernels": {"cg_fused_apply_ms": fa_ms, "cg_r_update_ms": fu_ms, "plain_apply_ms": apply_ms,
+                    "plain_apply_gbs": apply_bytes / (apply_ms * 1e-3) / 1e9 / world,
+                    "plain_apply_frac": apply_bytes / (apply_ms * 1e-3) / 1e9 / world / peak,
+                    "plain_apply_bytes_model": "34 B/node structured" if structured else "58 B/node + 32 B/cell"},
         "solve_roofline": {"achieved": solve_gbs, "peak": peak, "unit": "GB/s", "frac": solve_gbs / peak,
                            "bytes_per_iteration": iter_bytes},
     }

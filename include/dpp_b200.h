@@ -175,6 +175,11 @@ int dpp_host_free(void* ptr);
 /* mean device milliseconds of `reps` back-to-back applies of the monolithic operator on internal
  * vectors (after `warmup` untimed ones); with_dot fuses the (x, Ax) reduction as CG uses it. */
 int dpp_time_apply(dpp_handle h, int operator_mode, int warmup, int reps, int with_dot, double* mean_ms);
+/* mean device milliseconds of the two kernels of one fused Jacobi-CG iteration (uniform-grid path,
+ * csrc/cg_fused_uniform.cu), each timed alone over `reps` launches on the solver's work vectors:
+ * apply_ms = p/x update + matrix-free apply + <p,Ap> (+ row fix-up), update_ms = r update + <r,z>,<z,z>.
+ * Returns DPP_ERR_INVALID when the handle does not run the fused path. */
+int dpp_time_cg_kernels(dpp_handle h, int warmup, int reps, double* apply_ms, double* update_ms);
 int dpp_kernel_launch_count(dpp_handle h, int64_t* launches); /* kernels launched so far by this handle */
 
 #ifdef __cplusplus

@@ -149,6 +149,12 @@ class DppHandle:
                                              1 if with_dot else 0, C.byref(ms)), "dpp_time_apply")
         return ms.value
 
+    def time_cg_kernels(self, reps: int = 20, warmup: int = 3):
+        """(apply_ms, update_ms): the two kernels of one fused Jacobi-CG iteration, each timed alone."""
+        a, u = C.c_double(), C.c_double()
+        self._check(self._lib.dpp_time_cg_kernels(self._h, warmup, reps, C.byref(a), C.byref(u)), "dpp_time_cg_kernels")
+        return a.value, u.value
+
     def launch_count(self) -> int:
         n = C.c_int64()
         self._check(self._lib.dpp_kernel_launch_count(self._h, C.byref(n)), "dpp_kernel_launch_count")

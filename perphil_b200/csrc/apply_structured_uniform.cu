@@ -285,6 +285,28 @@ __global__ void k_fix_rows(const FixArgs a) {
 
 }  // namespace
 
+int structured_fix_rows(dpp_context* ctx, int nf, const int* fld, double* const* y, const double* const* xid,
+                        int identity, const double* skip_flag) {
+  FixArgs fx{};
+  for (int f = 0; f < nf; ++f) {
+    fx.nodes[f] = ctx->d_bc_nodes[fld[f]];
+    fx.count[f] = ctx->n_bc[fld[f]];
+    fx.y[f] = y[f];
+    fx.xid[f] = xid[f];
+  }
+  const long long total = fx.count[0] + fx.count[1];
+  if (total <= 0) return DPP_OK;
+  fx.identity = identity;
+  fx.ob = ctx->owned_begin;
+  fx.oe = ctx->owned_end;
+  fx.skip_flag = skip_flag;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 8));
+  k_fix_rows<<<blocks, 256, 0, ctx->stream>>>(fx);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+
 int structured_apply_uniform(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks) {
   const GridDesc& g = ctx->grid;
   const long long plane = (long long)g.n[1] * g.n[2];

@@ -190,6 +190,8 @@ int dpp_comm_init(dpp_handle ctx, int rank, int world, const void* unique_id, in
   ctx->world = world;
   ctx->owned_begin = owned_begin;
   ctx->owned_end = owned_end;
+  ctx->dom_lo = owned_begin == 0;            // a stored plane that is not owned is a ghost plane
+  ctx->dom_hi = owned_end == ctx->n_nodes;
   ctx->invalidate();
   if (world == 1) return DPP_OK;
   if (!unique_id) {

@@ -98,6 +98,7 @@ int dpp_create(dpp_handle* h, int device, int dim, int degree, int64_t n_nodes, 
     DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_partials, (int64_t)dpp::kMaxPartialBlocks * dpp::kMaxDotWidth));
     DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_scalars, dpp::kNumScalars));
     DPP_CUDA(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * dpp::kNumScalars, ctx->stream));
+    DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_dtab, 32));
     DPP_CUDA(cudaMallocHost((void**)&ctx->h_scalars, sizeof(double) * dpp::kNumScalars));
     std::memset(ctx->h_scalars, 0, sizeof(double) * dpp::kNumScalars);
     DPP_CHECK(dpp::structured_detect_and_setup(ctx, cnm, coords, ccnm));
@@ -121,7 +122,7 @@ void dpp_destroy(dpp_handle ctx) {
   dpp::comm_destroy(ctx);
   void* ptrs[] = {ctx->d_cnm, ctx->d_coords, ctx->ccnm_alias ? nullptr : ctx->d_ccnm, ctx->d_tables, ctx->d_adj_ptr,
                   ctx->d_adj_cell, ctx->d_adj_loc, ctx->d_cell_geom, ctx->d_mask, ctx->d_g, ctx->d_solution, ctx->d_diag,
-                  ctx->d_partials, ctx->d_scalars, ctx->d_hist[0], ctx->d_hist[1], ctx->d_premask, ctx->d_bc_nodes[0], ctx->d_bc_nodes[1]};
+                  ctx->d_partials, ctx->d_scalars, ctx->d_dtab, ctx->d_hist[0], ctx->d_hist[1], ctx->d_premask, ctx->d_bc_nodes[0], ctx->d_bc_nodes[1]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -372,6 +373,12 @@ int dpp_time_apply(dpp_handle ctx, int mode, int warmup, int reps, int with_dot,
   cudaEventDestroy(e1);
   *mean_ms = (double)ms / reps;
   return DPP_OK;
+}
+
+int dpp_time_cg_kernels(dpp_handle ctx, int warmup, int reps, double* apply_ms, double* update_ms) {
+  if (!ctx || reps <= 0 || warmup < 0 || !apply_ms || !update_ms) return DPP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  return dpp::krylov_time_cg_kernels(ctx, warmup, reps, apply_ms, update_ms);
 }
 
 int dpp_host_alloc(void** ptr, int64_t bytes) {

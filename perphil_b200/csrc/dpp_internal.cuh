@@ -116,6 +116,7 @@ struct dpp_context {
   // partition
   int rank = 0, world = 1;
   int64_t owned_begin = 0, owned_end = 0;
+  int dom_lo = 1, dom_hi = 1;     // first / last stored x-plane lies on the domain boundary (else: ghost plane)
   dpp::Comm* comm = nullptr;
 
   // work vectors / solver state (krylov.cu)
@@ -130,6 +131,7 @@ struct dpp_context {
   double* d_partials = nullptr;   // [kMaxPartialBlocks * kMaxDotWidth]
   double* d_scalars = nullptr;    // device scalar block
   double* h_scalars = nullptr;    // pinned mirror
+  double* d_dtab = nullptr;       // [2 slots][16] reciprocal-diagonal class tables of the fused CG
   double* d_hist[2] = {nullptr, nullptr};  // residual history per solver slot
   int hist_cap[2] = {0, 0};
 
@@ -149,6 +151,10 @@ int structured_detect_and_setup(dpp_context* ctx, const int32_t* cnm_host, const
 int structured_apply(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks);
 int structured_diagonal(dpp_context* ctx, const Coef& c, double* d_diag /*[2*n_nodes]*/);
 int structured_apply_uniform(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks);
+// row elimination after a uniform-grid apply: y_f[node] = identity ? xid_f[node] : 0 on the constrained
+// nodes of mask field fld[f] (owned rows only)
+int structured_fix_rows(dpp_context* ctx, int nf, const int* fld, double* const* y, const double* const* xid,
+                        int identity, const double* skip_flag);
 
 // ---- apply_general.cu
 int general_setup(dpp_context* ctx, const int32_t* cnm_host);
@@ -183,6 +189,7 @@ void csr_destroy(dpp_context* ctx);
 int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_result* res,
                  double* hist_host, int32_t hist_cap);
 void krylov_destroy(dpp_context* ctx);
+int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply_ms, double* update_ms);
 
 template <typename T>
 inline int dev_alloc(dpp_context* ctx, T** p, int64_t count) {

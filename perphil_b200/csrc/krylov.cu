@@ -157,13 +157,59 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
   DPP_CHECK(scalars_init(ctx, slot, tol.rtol, tol.atol, tol.dtol, tol.max_it, std::min(hist_cap, ctx->hist_cap[slot])));
   DPP_CHECK(vec_zero(ctx, x, len));
   DPP_CHECK(vec_copy(ctx, wk.r, b, len));
+  const double* h = ctx->h_scalars + (size_t)slot * S_SLOT_SIZE;
+  if (fused && cg_fused_available(ctx, op.nf, op.mode, pc.type)) {
+    // two kernels per iteration (cg_fused_uniform.cu): p, x updates live inside the apply kernel
+    const int64_t n = ctx->n_nodes;
+    const Coef coef = op.nf == 2 ? dpp_coef(ctx) : block_coef(ctx, op.row, op.col);
+    double* dtab = ctx->d_dtab + (size_t)slot * 16;
+    double* P[2] = {wk.p, wk.z};
+    DPP_CHECK(cg_fused_table(ctx, coef, op.nf, pc.type, dtab));
+    DPP_CHECK(vec_zero(ctx, P[0], len));
+    DPP_CHECK(vec_zero(ctx, P[1], len));
+    DPP_CHECK(halo(ctx, wk.r, op.nf));
+    int nb = 0;
+    DPP_CHECK(cg_fused_rz_init(ctx, L, wk.r, slot, dtab, &nb));
+    DPP_CHECK(reduce_partials(ctx, nb, 2, slot, POST_CG_INIT));
+    DPP_CHECK(scalars_fetch(ctx, slot));
+    const int fld[2] = {op.nf == 2 ? 0 : op.row, 1};
+    const int every = std::max(1, check_every);
+    long long kk = 0;
+    while (h[S_REASON] == 0.0) {
+      for (int k = 0; k < every; ++k, ++kk) {
+        const double* pin[2] = {P[kk & 1], P[kk & 1] + n};
+        double* pout[2] = {P[(kk + 1) & 1], P[(kk + 1) & 1] + n};
+        const double* rr[2] = {wk.r, wk.r + n};
+        double* xx[2] = {x, x + n};
+        double* ww[2] = {wk.w, wk.w + n};
+        DPP_CHECK(cg_fused_apply(ctx, op.nf, coef, rr, pin, pout, xx, ww, slot, dtab, &nb));
+        ctx->krylov->apply_count++;
+        DPP_CHECK(structured_fix_rows(ctx, op.nf, fld, ww, pout, 1, S + S_REASON));
+        DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
+        DPP_CHECK(cg_fused_r_update(ctx, L, wk.r, wk.w, slot, dtab, &nb));
+        DPP_CHECK(reduce_partials(ctx, nb, 2, slot, POST_CG_RZ));
+        DPP_CHECK(halo(ctx, wk.r, op.nf));
+      }
+      DPP_CHECK(scalars_fetch(ctx, slot));
+    }
+    DPP_CHECK(cg_fused_x_finalize(ctx, L, x, P[(long long)h[S_ITS] & 1], slot));
+    out->its = (int)h[S_ITS];
+    out->reason = (int)h[S_REASON];
+    out->rnorm = h[S_RNORM];
+    const int nh = std::min(out->its + 1, std::min(hist_cap, ctx->hist_cap[slot]));
+    out->hist.resize(std::max(nh, 0));
+    if (nh > 0) {
+      DPP_CUDA(cudaMemcpyAsync(out->hist.data(), ctx->d_hist[slot], sizeof(double) * nh, cudaMemcpyDeviceToHost, ctx->stream));
+      DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return DPP_OK;
+  }
   if (fused) {
     DPP_CHECK(vec_pointwise_mult(ctx, L, dinv, wk.r, wk.z));
   } else {
     DPP_CHECK(pc_apply(ctx, pc, wk.r, wk.z));
   }
   DPP_CHECK(vec_dot2(ctx, L, wk.r, wk.z, wk.z, wk.z, slot, POST_CG_INIT));
-  const double* h = ctx->h_scalars + (size_t)slot * S_SLOT_SIZE;
   DPP_CHECK(scalars_fetch(ctx, slot));
   const int every = fused ? std::max(1, check_every) : 1;
   while (h[S_REASON] == 0.0) {
@@ -489,6 +535,75 @@ int krylov_work_vectors(dpp_context* ctx, double** a, double** b) {
   DPP_CHECK(ensure_work(ctx));
   *a = ctx->krylov->p;
   *b = ctx->krylov->w;
+  return DPP_OK;
+}
+
+__global__ void k_fill_work(long long n, double* __restrict__ x, const uint8_t* __restrict__ mask, unsigned long long salt) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long z = ((unsigned long long)i + salt) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    z ^= z >> 29; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 32;
+    x[i] = mask[i] ? 0.0 : (double)(z & 0xFFFFF) / 1048576.0 - 0.5;
+  }
+}
+
+int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply_ms, double* update_ms) {
+  if (!ctx->have_params) {
+    ctx->set_error("dpp_time_cg_kernels: call dpp_set_params first");
+    return DPP_ERR_STATE;
+  }
+  if (!cg_fused_available(ctx, 2, DPP_OP_MATRIX_FREE, DPP_PC_JACOBI)) {
+    ctx->set_error("dpp_time_cg_kernels: the handle does not run the fused uniform-grid CG path");
+    return DPP_ERR_INVALID;
+  }
+  DPP_CHECK(ensure_work(ctx));
+  Krylov* K = ctx->krylov;
+  const int64_t n = ctx->n_nodes;
+  const VecLayout L = layout(ctx, 2);
+  const int slot = 0;
+  double* S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
+  double* vs[4] = {K->r, K->p, K->z, K->x};
+  for (int v = 0; v < 4; ++v) {
+    k_fill_work<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(2 * n, vs[v], ctx->d_mask, 7919ull * (v + 1));
+    ctx->launches++;
+  }
+  DPP_CHECK(scalars_init(ctx, slot, 1e-8, 1e-12, 1e4, 1 << 30, 0));
+  double* hs = ctx->h_scalars + (size_t)slot * S_SLOT_SIZE;
+  hs[S_ITS] = 1.0; hs[S_RZ] = 1.0; hs[S_RZ_OLD] = 2.0; hs[S_PAP] = 1.0; hs[S_ALPHA] = 1e-3; hs[S_XPEND] = 1.0;
+  hs[S_RTOL] = 1e-8; hs[S_ATOL] = 1e-12; hs[S_DTOL] = 1e4; hs[S_MAXIT] = (double)(1 << 30);
+  DPP_CUDA(cudaMemcpyAsync(S, hs, sizeof(double) * S_SLOT_SIZE, cudaMemcpyHostToDevice, ctx->stream));
+  DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  const Coef coef = dpp_coef(ctx);
+  double* dtab = ctx->d_dtab;
+  DPP_CHECK(cg_fused_table(ctx, coef, 2, DPP_PC_JACOBI, dtab));
+  const double* rr[2] = {K->r, K->r + n};
+  double* xx[2] = {K->x, K->x + n};
+  double* ww[2] = {K->w, K->w + n};
+  double* P[2] = {K->p, K->z};
+  const int fld[2] = {0, 1};
+  cudaEvent_t e0, e1;
+  DPP_CUDA(cudaEventCreate(&e0));
+  DPP_CUDA(cudaEventCreate(&e1));
+  float ms = 0;
+  int nb = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int i = -warmup; i < reps; ++i) {
+      if (i == 0) DPP_CUDA(cudaEventRecord(e0, ctx->stream));
+      if (pass == 0) {
+        const double* pin[2] = {P[i & 1], P[i & 1] + n};
+        double* pout[2] = {P[(i + 1) & 1], P[(i + 1) & 1] + n};
+        DPP_CHECK(cg_fused_apply(ctx, 2, coef, rr, pin, pout, xx, ww, slot, dtab, &nb));
+        DPP_CHECK(structured_fix_rows(ctx, 2, fld, ww, pout, 1, S + S_REASON));
+      } else {
+        DPP_CHECK(cg_fused_r_update(ctx, L, K->r, K->w, slot, dtab, &nb));
+      }
+    }
+    DPP_CUDA(cudaEventRecord(e1, ctx->stream));
+    DPP_CUDA(cudaEventSynchronize(e1));
+    DPP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *(pass == 0 ? apply_ms : update_ms) = (double)ms / reps;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return DPP_OK;
 }
 

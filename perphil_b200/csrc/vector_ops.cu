@@ -49,9 +49,16 @@ __device__ __forceinline__ Chunk my_chunk(const VecLayout& L) {
 __device__ void apply_post(double* S, double* hist, int post) {
   // executed by one thread after the reduction values are in S[S_TMP..]
   if (post == POST_CG_PAP) {
+    if (S[S_REASON] != 0.0) return;  // the apply was a no-op: partials are stale
     const double pap = S[S_TMP];
     S[S_PAP] = pap;
-    if (S[S_REASON] == 0.0 && !(pap > 0.0)) S[S_REASON] = (pap == pap) ? DPP_DIVERGED_INDEFINITE_MAT : DPP_DIVERGED_NANORINF;
+    if (!(pap > 0.0)) {
+      S[S_REASON] = (pap == pap) ? DPP_DIVERGED_INDEFINITE_MAT : DPP_DIVERGED_NANORINF;
+      S[S_XPEND] = 0.0;
+    } else {
+      S[S_ALPHA] = S[S_RZ] / pap;
+      S[S_XPEND] = 1.0;
+    }
     return;
   }
   if (post == POST_CG_INIT || post == POST_CG_RZ) {

@@ -12,7 +12,7 @@ namespace dpp {
 // layout of one solver slot in ctx->d_scalars (doubles)
 enum {
   S_RZ = 0, S_RZ_OLD, S_PAP, S_ZZ, S_TTOL, S_RNORM0, S_ITS, S_REASON, S_RNORM, S_DTOL, S_MAXIT, S_ATOL,
-  S_RTOL, S_HISTCAP, S_SPARE0, S_SPARE1, S_TMP /* 40 doubles of reduction output */, S_SLOT_SIZE = 64
+  S_RTOL, S_HISTCAP, S_ALPHA /* rz / pAp of the current iteration */, S_XPEND /* x += alpha p not applied yet */, S_TMP /* 40 doubles of reduction output */, S_SLOT_SIZE = 64
 };
 
 enum PostOp { POST_NONE = 0, POST_CG_INIT = 1, POST_CG_PAP = 2, POST_CG_RZ = 3 };
@@ -45,6 +45,17 @@ int cg_p_update(dpp_context* ctx, const VecLayout& L, double* p, const double* r
                 const double* z, int slot);
 int cg_xr_update(dpp_context* ctx, const VecLayout& L, double* x, double* r, const double* p, const double* w,
                  const double* dinv, bool fused_pc, int slot, PostOp post);
+
+// fused CG iteration on uniform grids (cg_fused_uniform.cu)
+bool cg_fused_available(const dpp_context* ctx, int nf, int operator_mode, int pc_type);
+int cg_fused_table(dpp_context* ctx, const Coef& c, int nf, int pc_type, double* d_tab);
+int cg_fused_rz_init(dpp_context* ctx, const VecLayout& L, const double* r, int slot, const double* dtab, int* nblocks);
+int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, const double* const* r, const double* const* pin,
+                   double* const* pout, double* const* x, double* const* w, int slot, const double* dtab,
+                   int* n_partial_blocks);
+int cg_fused_r_update(dpp_context* ctx, const VecLayout& L, double* r, const double* w, int slot, const double* dtab,
+                      int* nblocks);
+int cg_fused_x_finalize(dpp_context* ctx, const VecLayout& L, double* x, const double* p, int slot);
 
 // GMRES kernels
 int gmres_mdot(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, const double* w, int slot);

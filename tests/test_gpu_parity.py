@@ -378,3 +378,73 @@ def test_solve_128_residual_and_convergence():
     Au = h.apply(u)
     interior = np.ones(2 * n, bool); interior[b] = False; interior[n + b] = False
     assert np.linalg.norm((dinv * Au)[interior]) <= 10 * 1e-8 * info.history[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# fused CG iteration (csrc/cg_fused_uniform.cu) vs the unfused kernel sequence and the oracle
+# ---------------------------------------------------------------------------------------------
+
+def _solve_vec(W, p, bcs, params):
+    sol = pb.solve_dpp(W, p, bcs, solver_parameters=params)
+    u = np.concatenate([sol.solution.sub(0).dat.data, sol.solution.sub(1).dat.data]).copy()
+    return sol, u, pb.last_solve_info()
+
+
+@pytest.mark.parametrize("cells", [(8, 8, 8), (33, 9, 40), (5, 7, 9), (37, 5), (16, 16), (1, 1, 1), (2, 1, 3)])
+@pytest.mark.parametrize("preset", ["jacobi", "none"])
+def test_fused_cg_equals_unfused_sequence(cells, preset, monkeypatch):
+    """Same iteration count, same residual history (to rounding) and same solution whether the CG
+    iteration runs as 2 fused kernels or as the apply / xr-update / p-update sequence."""
+    W, p, bcs, osys = make_problem(cells, 1)
+    params = {**(pb.B200_CG_JACOBI_PARAMS if preset == "jacobi" else pb.B200_CG_PARAMS), "b200_history": 4096}
+    monkeypatch.delenv("DPP_NO_FUSED_CG", raising=False)
+    s1, u1, i1 = _solve_vec(W, p, bcs, params)
+    monkeypatch.setenv("DPP_NO_FUSED_CG", "1")
+    s2, u2, i2 = _solve_vec(W, p, bcs, params)
+    monkeypatch.delenv("DPP_NO_FUSED_CG", raising=False)
+    if preset == "jacobi":
+        assert s1.iteration_number == s2.iteration_number
+        assert np.allclose(i1.history, i2.history, rtol=1e-9, atol=0)
+    else:
+        assert its_close(s1.iteration_number, s2.iteration_number)
+    assert i1.converged_reason == i2.converged_reason
+    if osys.interior.sum() > 0:
+        assert rel_err(u1, u2) < 1e-8
+    ref = orc.solve_dpp_oracle(osys, "cg", preset)
+    assert rel_err(u1, ref.u) < 1e-7
+
+
+def test_fused_cg_partial_and_no_dirichlet():
+    """Boundary nodes that are NOT constrained use the boundary-class reciprocal diagonal."""
+    cells = (6, 5, 7)
+    mesh = pb.UnitCubeMesh(*cells)
+    _, V = pb.create_function_spaces(mesh)
+    W = V * V
+    prm = pb.DPPParameters(k1=2.0, k2=0.3, beta=1.5, mu=0.7)
+    omesh = orc.structured_mesh(cells, 1)
+    X = V.node_coordinates
+    face = np.flatnonzero(X[:, 0] == 0.0).astype(np.int32)          # only the x = 0 face, field 0
+    edge = np.flatnonzero((X[:, 1] == 1.0)).astype(np.int32)        # y = 1 face, field 1
+    g0 = 1.0 + X[face, 1]
+    g1 = 2.0 - X[edge, 2]
+    osys = orc.build_system(omesh, orc.Params(k1=2.0, k2=0.3, beta=1.5, mu=0.7), (face, g0, edge, g1))
+    h = pb.handle_for(W)
+    h.set_params(2.0, 0.3, 1.5, 0.7)
+    h.set_dirichlet(0, face, g0)
+    h.set_dirichlet(1, edge, g1)
+    ref = orc.solve_dpp_oracle(osys, "cg", "jacobi")
+    opt = h.default_options()
+    u, info = h.solve(opt, want_solution=True, history=512)
+    assert info.iterations == ref.iteration_number
+    assert np.allclose(info.history, ref.history, rtol=1e-7)
+    assert rel_err(u, ref.u) < 1e-9
+
+
+def test_fused_cg_kernel_timer_runs():
+    W, p, bcs, _ = make_problem((16, 16, 16), 1)
+    h = configured_handle(W, p, bcs)
+    a, u = h.time_cg_kernels(reps=3, warmup=1)
+    assert a > 0 and u > 0
+    # the timer scribbles on the work vectors only: a solve afterwards is unaffected
+    sol = pb.solve_dpp(W, p, bcs, solver_parameters=pb.B200_CG_JACOBI_PARAMS)
+    assert sol.iteration_number == 31
