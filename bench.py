@@ -234,13 +234,13 @@ def main():
     apply_bytes = 34 * n_nodes_global if structured else 58 * n_nodes_global + 32 * N ** 3
     fused = structured
     try:
-        fa_ms, fu_ms = h.time_cg_kernels(reps=20, warmup=3)
+        fa_ms, fu_ms, mv_ms = h.time_cg_kernels(reps=20, warmup=3)
     except Exception:
-        fused, fa_ms, fu_ms = False, None, None
+        fused, fa_ms, fu_ms, mv_ms = False, None, None, None
     if comm is not None:
         apply_ms = comm.max_float(apply_ms)
         if fused:
-            fa_ms, fu_ms = comm.max_float(fa_ms), comm.max_float(fu_ms)
+            fa_ms, fu_ms, mv_ms = comm.max_float(fa_ms), comm.max_float(fu_ms), comm.max_float(mv_ms)
     if fused:
         # k_cg_fused_apply: reads r, p_old, x and writes p, A p, x (6 passes of 8 B per DoF) + the 1 B/DoF
         # Dirichlet information (row fix-up list); k_cg_r_update: reads r, A p, writes r (3 passes)
@@ -269,7 +269,9 @@ def main():
                    "kernel_family": "structured" if structured else "general"},
         "iterations": its, "residual_error": sol.residual_error, "wall_ms_per_step": wall_ms,
         "tts_mdofs": ndof / (ms * 1e-3) / 1e6,
-        "matvec_gdofs": ndof / (apply_ms * 1e-3) / 1e9, "matvec_ms": apply_ms,
+        "matvec_gdofs": ndof / ((mv_ms if fused else apply_ms) * 1e-3) / 1e9, "matvec_ms": mv_ms if fused else apply_ms,
+        "matvec_gbs": apply_bytes / ((mv_ms if fused else apply_ms) * 1e-3) / 1e9 / world,
+        "matvec_roofline_frac": apply_bytes / ((mv_ms if fused else apply_ms) * 1e-3) / 1e9 / world / peak,
         "e2e": {"value": ndof * its / (e2e_ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
@@ -278,7 +280,7 @@ def main():
                      "frac": achieved / peak, "traffic": TRAFFIC_NCU.get("fused_apply") if fused else None,
                      "peak_kind": peak_kind, "bytes_model": bytes_model, "algorithmic_bytes": dom_bytes,
                      "ms_per_launch": dom_ms},
-        "kernels": {"cg_fused_apply_ms": fa_ms, "cg_r_update_ms": fu_ms, "plain_apply_ms": apply_ms,
+        "kernels": {"cg_fused_apply_ms": fa_ms, "cg_r_update_ms": fu_ms, "tma_matvec_ms": mv_ms, "plain_apply_ms": apply_ms,
                     "plain_apply_gbs": apply_bytes / (apply_ms * 1e-3) / 1e9 / world,
                     "plain_apply_frac": apply_bytes / (apply_ms * 1e-3) / 1e9 / world / peak,
                     "plain_apply_bytes_model": "34 B/node structured" if structured else "58 B/node + 32 B/cell"},

@@ -177,9 +177,10 @@ int dpp_host_free(void* ptr);
 int dpp_time_apply(dpp_handle h, int operator_mode, int warmup, int reps, int with_dot, double* mean_ms);
 /* mean device milliseconds of the two kernels of one fused Jacobi-CG iteration (uniform-grid path,
  * csrc/cg_fused_uniform.cu), each timed alone over `reps` launches on the solver's work vectors:
- * apply_ms = p/x update + matrix-free apply + <p,Ap> (+ row fix-up), update_ms = r update + <r,z>,<z,z>.
+ * apply_ms = p/x update + matrix-free apply + <p,Ap> (+ row fix-up), update_ms = r update + <r,z>,<z,z>,
+ * matvec_ms = the same TMA kernel in plain mode (w = A p, fused <p,Ap>: PETSc MatMult on the path).
  * Returns DPP_ERR_INVALID when the handle does not run the fused path. */
-int dpp_time_cg_kernels(dpp_handle h, int warmup, int reps, double* apply_ms, double* update_ms);
+int dpp_time_cg_kernels(dpp_handle h, int warmup, int reps, double* apply_ms, double* update_ms, double* matvec_ms);
 int dpp_kernel_launch_count(dpp_handle h, int64_t* launches); /* kernels launched so far by this handle */
 
 #ifdef __cplusplus

@@ -73,7 +73,8 @@ _PROTOTYPES = {
                             C.c_int32]),
     "dpp_solution_dev": (C.c_void_p, [C.c_void_p]),
     "dpp_time_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
-    "dpp_time_cg_kernels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "dpp_time_cg_kernels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double)]),
     "dpp_kernel_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "dpp_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "dpp_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),

@@ -150,10 +150,12 @@ class DppHandle:
         return ms.value
 
     def time_cg_kernels(self, reps: int = 20, warmup: int = 3):
-        """(apply_ms, update_ms): the two kernels of one fused Jacobi-CG iteration, each timed alone."""
-        a, u = C.c_double(), C.c_double()
-        self._check(self._lib.dpp_time_cg_kernels(self._h, warmup, reps, C.byref(a), C.byref(u)), "dpp_time_cg_kernels")
-        return a.value, u.value
+        """(apply_ms, update_ms, matvec_ms): the two kernels of one fused Jacobi-CG iteration and the plain
+        matrix-free apply of the same (TMA, padded-layout) kernel, each timed alone."""
+        a, u, m = C.c_double(), C.c_double(), C.c_double()
+        self._check(self._lib.dpp_time_cg_kernels(self._h, warmup, reps, C.byref(a), C.byref(u), C.byref(m)),
+                    "dpp_time_cg_kernels")
+        return a.value, u.value, m.value
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -76,15 +76,25 @@ __global__ void __launch_bounds__(NT, 2) k_apply_uniform(const UArgs s) {
   __shared__ double red[TY];
 
   const int ni = s.n[0], nj = s.n[1], nk = s.n[2];
-  const int tile = blockIdx.x;
+  const int nown = s.i_end - s.i_begin;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * TK + tx;
+  double dot = 0.0;
+  // Balanced persistent partition: the (tile, plane) steps of the whole grid are cut into gridDim.x equal
+  // contiguous ranges (one CTA each, a single wave of 2 CTAs per SM); a range is processed as runs of
+  // consecutive planes of one tile (2 redundant planes per run).
+  const long long total = (long long)s.ntj * s.ntk * nown;
+  long long wbeg = (total * blockIdx.x) / gridDim.x;
+  const long long wend = (total * (blockIdx.x + 1)) / gridDim.x;
+  for (; wbeg < wend;) {
+  const int tile = (int)(wbeg / nown);
+  const int run_a = (int)(wbeg - (long long)tile * nown);
+  const int run_len = (int)((wend - wbeg) < (long long)(nown - run_a) ? (wend - wbeg) : (long long)(nown - run_a));
+  wbeg += run_len;
+  const int i_lo = s.i_begin + run_a, i_hi = i_lo + run_len;
   const int tkid = tile % s.ntk, tjid = tile / s.ntk;
   const int k0 = bstart(tkid, nk, s.ntk), k1 = bstart(tkid + 1, nk, s.ntk);
   const int j0 = bstart(tjid, nj, s.ntj), j1 = bstart(tjid + 1, nj, s.ntj);
-  const int nown = s.i_end - s.i_begin;
-  const int i_lo = s.i_begin + bstart(blockIdx.y, nown, s.nseg);
-  const int i_hi = s.i_begin + bstart(blockIdx.y + 1, nown, s.nseg);
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int tid = ty * TK + tx;
   const int jA = j0 + 2 * ty, jB = jA + 1, k = k0 + tx;
   const bool actA = (jA < j1) && (k < k1), actB = (jB < j1) && (k < k1);
   const long long plane = (long long)nj * nk;
@@ -170,9 +180,9 @@ __global__ void __launch_bounds__(NT, 2) k_apply_uniform(const UArgs s) {
       for (int d = 0; d < 3; ++d) qc[f][r][d] = qd[f][r][d] = 0.0;
       prev_cen[f][r] = 0.0;
     }
-  double dot = 0.0;
   const double* tbase = &xs[0][0][2 * ty * SROW + tx];
 
+  __syncthreads();  // the ring is free (previous run of this CTA finished)
   // prologue: planes i_first (slot 2) and i_first+1 (slot 0) in flight
   DPP_ISSUE(2)
   DPP_ISSUE(0)
@@ -240,6 +250,7 @@ __global__ void __launch_bounds__(NT, 2) k_apply_uniform(const UArgs s) {
 #undef DPP_STEP
 #undef DPP_ISSUE
   cp_async_wait<0>();
+  }  // runs
 
   if (s.dot_partials != nullptr) {
 #pragma unroll
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(NT, 2) k_apply_uniform(const UArgs s) {
       double t = 0.0;
 #pragma unroll
       for (int w = 0; w < TY; ++w) t += red[w];
-      s.dot_partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+      s.dot_partials[blockIdx.x] = t;
     }
   }
 }
@@ -358,17 +369,12 @@ int structured_apply_uniform(dpp_context* ctx, const OpArgs& a, int* n_partial_b
     if (n_partial_blocks) *n_partial_blocks = 0;
     return DPP_OK;
   }
-  // x-segments: about two full waves of resident CTAs (2 per SM), at least 8 planes per segment
-  const int capacity = ctx->sm_count * 2;
-  int nseg = (2 * capacity + tiles / 2) / tiles;
-  nseg = std::max(1, std::min(nseg, std::max(1, nown / 8)));
-  while ((long long)tiles * nseg > kMaxPartialBlocks && nseg > 1) --nseg;
-  if ((long long)tiles * nseg > kMaxPartialBlocks * (long long)kMaxDotWidth && a.dot_partials != nullptr) {
-    ctx->set_error("structured apply: too many tiles for the reduction scratch");
-    return DPP_ERR_INVALID;
-  }
-  s.nseg = nseg;
-  dim3 grid(tiles, nseg), block(TK, TY);
+  // one wave of persistent CTAs (2 per SM) with equal shares of the (tile, plane) steps; small grids
+  // get fewer CTAs so that a run stays >= ~8 planes
+  const long long total = (long long)tiles * nown;
+  const int nctas = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count * 2, total / 8));
+  s.nseg = 1;
+  dim3 grid(nctas), block(TK, TY);
   if (a.nf == 2)
     k_apply_uniform<2><<<grid, block, 0, ctx->stream>>>(s);
   else
@@ -386,7 +392,7 @@ int structured_apply_uniform(dpp_context* ctx, const OpArgs& a, int* n_partial_b
     ctx->launches++;
     DPP_CUDA(cudaGetLastError());
   }
-  if (n_partial_blocks) *n_partial_blocks = tiles * nseg;
+  if (n_partial_blocks) *n_partial_blocks = nctas;
   return DPP_OK;
 }
 

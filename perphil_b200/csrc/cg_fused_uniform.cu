@@ -10,11 +10,21 @@
 // The reciprocal diagonal is never read from memory: on a uniform grid diag(A) takes one of 8 values
 // per field (node on the domain boundary of axis x/y/z or not), kept in a 16-entry table.
 //
-// The apply part is the kernel of apply_structured_uniform.cu (cp.async ring of planes, two nodes
-// per thread, register queue along x); what changes is that the stencil input p is formed on chip:
-// each thread combines exactly the elements it copied itself (its two nodes + at most one halo
-// node), p = dinv*r + beta*p_old, in place in the shared ring before the per-plane barrier.
+// Data layout.  The vectors of this path live in a PADDED layout private to the library: row pitch
+// (z direction) rounded up to 16 doubles, so that every row starts on a 128-byte boundary and the
+// arrays are legal TMA tensors (16-byte strides).  The pad columns are zero and stay zero.
+//
+// Data movement.  Plane tiles (18 x 34 nodes incl. halo, both fields) are fetched with ONE TMA tensor
+// load per array (cp.async.bulk.tensor.4d, SASS UTMALDG) into a 3-slot shared-memory ring, completion
+// on an mbarrier per slot; out-of-domain halo nodes are zero-filled by the TMA unit.  No per-thread
+// address arithmetic, no LSU traffic for the loads (the cp.async/LDGSTS predecessor of this kernel was
+// bound by the LSU pipe and by 8-byte copy granularity at ~50 % of HBM peak; profiles/).
+// The stencil part is the one of apply_structured_uniform.cu: two nodes per thread, in-plane
+// neighbour-class sums, register queue along x, fused <p, A p>.
+#include <cuda.h>
+
 #include <algorithm>
+#include <cstdlib>
 
 #include "vector_ops.cuh"
 
@@ -26,231 +36,264 @@ constexpr int TK = 32;
 constexpr int TY = 8;
 constexpr int TJ = 2 * TY;
 constexpr int NT = TK * TY;
-constexpr int SROW = TK + 2;
-constexpr int SLOT = (TJ + 2) * SROW;
+// TMA needs the innermost box coordinate on a 16-byte boundary (probed on B200: an odd fp64 coordinate
+// raises 'illegal instruction'), so tiles start at even k and the halo'd box starts at k0-2: 36 columns,
+// column c of a slot row holds node k0 - 2 + c (columns 0 and 35 are fetched but never used).
+constexpr int SROW = TK + 4;
+constexpr int SLOT = (TJ + 2) * SROW;   // doubles per field per ring slot (halo'd tile)
 constexpr int XSLOT = TJ * TK;
-constexpr int HALO = 2 * SROW + 2 * TJ;
 constexpr int RING = 3;
 
 struct FArgs {
   int n[3];
+  int pitch;                 // padded row length (doubles)
+  long long plane, field;    // padded plane / field strides (doubles)
   const double* m1d[3];
   const double* k1d[3];
   double mo[3], ko[3];
   double mxc_i, mxc_b, kxc_i, kxc_b;
-  const double* r[2];
-  const double* pin[2];   // p of the previous iteration (ghost planes valid)
-  double* pout[2];        // p of this iteration (own + ghost planes written)
-  double* x[2];
-  double* w[2];
+  double* pout;              // p of this iteration (own + ghost planes written)   [padded, field-blocked]
+  double* x;
+  double* w;
   Coef c;
   double* dot_partials;
   int i_begin, i_end;
-  int ntj, ntk, nseg;
-  const double* S;        // scalar slot of the solver
-  const double* dtab;     // [2][8] reciprocal diagonal per boundary class bx*4 + by*2 + bz
-  int dom_lo, dom_hi;     // local plane 0 / n[0]-1 lies on the domain boundary (else it is a ghost plane)
+  int ntj, ntk;
+  const double* S;           // scalar slot of the solver (null in plain-apply mode)
+  const double* dtab;        // [2][8] reciprocal diagonal per boundary class bx*4 + by*2 + bz
+  int dom_lo, dom_hi;        // local plane 0 / n[0]-1 lies on the domain boundary (else it is a ghost plane)
 };
 
 __device__ __forceinline__ int bstart(int t, int n, int nt) { return (int)(((long long)t * n) / nt); }
 
-__device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* gptr, bool valid) {
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned addr, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
   asm volatile(
-      "{\n .reg .pred p;\n setp.eq.u32 p, %2, 0;\n cp.async.ca.shared.global [%0], [%1], 8, p;\n}\n" ::"r"(smem_addr),
-      "l"(gptr), "r"((unsigned)valid)
+      "{\n .reg .pred P1;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE_%=;\n"
+      " bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(addr),
+      "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, unsigned mbar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 template <int NF>
-struct Smem {
-  double r[RING][NF][SLOT];
-  double p[RING][NF][SLOT];
-  double x[RING][NF][XSLOT];
+struct __align__(128) Smem {
+  static constexpr int RS = ((NF * SLOT * 8 + 127) / 128) * 16;   // doubles per slot, 128-byte multiple
+  double r[RING][RS];
+  double p[RING][RS];
+  double x[RING][NF * XSLOT];
+  unsigned long long mbar[RING];
   double red[TY];
   double dtab[16];
 };
 
-template <int NF>
-__global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s) {
-  if (s.S[S_REASON] != 0.0) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// FUSED = true : CG iteration kernel (p = dinv r + beta p_old formed on chip, deferred x update, p stored)
+// FUSED = false: plain apply w = A p on padded vectors (tm_p = input), optional <p, w>
+template <int NF, bool FUSED>
+__global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const __grid_constant__ CUtensorMap tm_r,
+                                                          const __grid_constant__ CUtensorMap tm_p,
+                                                          const __grid_constant__ CUtensorMap tm_x) {
+  if (FUSED && s.S[S_REASON] != 0.0) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem<NF>& sm = *reinterpret_cast<Smem<NF>*>(smem_raw);
+  constexpr int RS = Smem<NF>::RS;
 
   const int ni = s.n[0], nj = s.n[1], nk = s.n[2];
-  const int tile = blockIdx.x;
-  const int tkid = tile % s.ntk, tjid = tile / s.ntk;
-  const int k0 = bstart(tkid, nk, s.ntk), k1 = bstart(tkid + 1, nk, s.ntk);
-  const int j0 = bstart(tjid, nj, s.ntj), j1 = bstart(tjid + 1, nj, s.ntj);
   const int nown = s.i_end - s.i_begin;
-  const int i_lo = s.i_begin + bstart(blockIdx.y, nown, s.nseg);
-  const int i_hi = s.i_begin + bstart(blockIdx.y + 1, nown, s.nseg);
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * TK + tx;
-  const int jA = j0 + 2 * ty, jB = jA + 1, k = k0 + tx;
-  const bool actA = (jA < j1) && (k < k1), actB = (jB < j1) && (k < k1);
-  const long long plane = (long long)nj * nk;
-  const int i_first = i_lo - 1;
-  // planes whose p this CTA stores: its output planes, plus a ghost plane next to the first/last segment
-  const int pw_lo = (blockIdx.y == 0 && s.i_begin > 0) ? i_lo - 1 : i_lo;
-  const int pw_hi = (blockIdx.y == gridDim.y - 1 && s.i_end < ni) ? i_hi + 1 : i_hi;
-
-  if (tid < 16) sm.dtab[tid] = (tid < 8 * NF) ? s.dtab[tid] : 1.0;
-
-  const bool ownA_ok = (jA < nj) && (k < nk), ownB_ok = (jB < nj) && (k < nk);
-  const long long own_off = (long long)jA * nk + k;
-  int hr = 0, hc = 0;
-  bool halo_ok = false;
-  const bool is_halo = tid < HALO;
-  if (is_halo) {
-    if (tid < SROW) { hr = 0; hc = tid; }
-    else if (tid < 2 * SROW) { hr = TJ + 1; hc = tid - SROW; }
-    else if (tid < 2 * SROW + TJ) { hr = tid - 2 * SROW + 1; hc = 0; }
-    else { hr = tid - 2 * SROW - TJ + 1; hc = TK + 1; }
-    const int jj = j0 - 1 + hr, kk = k0 - 1 + hc;
-    halo_ok = (jj >= 0) && (jj < nj) && (kk >= 0) && (kk < nk);
-  }
-  const int jH = j0 - 1 + hr, kH = k0 - 1 + hc;
-  const long long halo_delta = halo_ok ? ((long long)jH * nk + kH) - own_off : 0;
-  const int own_e = (2 * ty + 1) * SROW + tx + 1;   // element index of node A inside a slot
-  const int halo_e = hr * SROW + hc;
-  const int xown_e = 2 * ty * TK + tx;
-  const unsigned sr_base = (unsigned)__cvta_generic_to_shared(&sm.r[0][0][0]);
-  const unsigned sp_base = (unsigned)__cvta_generic_to_shared(&sm.p[0][0][0]);
-  const unsigned sx_base = (unsigned)__cvta_generic_to_shared(&sm.x[0][0][0]);
-
-  // boundary class (y,z part) of the three nodes this thread combines
-  const int clsA = ((jA == 0 || jA == nj - 1) ? 2 : 0) + ((k == 0 || k == nk - 1) ? 1 : 0);
-  const int clsB = ((jB == 0 || jB == nj - 1) ? 2 : 0) + ((k == 0 || k == nk - 1) ? 1 : 0);
-  const int clsH = ((jH == 0 || jH == nj - 1) ? 2 : 0) + ((kH == 0 || kH == nk - 1) ? 1 : 0);
-
-  // scalars of the iteration (device resident; written by the reduction epilogues)
-  const double beta = (s.S[S_ITS] == 0.0) ? 0.0 : s.S[S_RZ] / s.S[S_RZ_OLD];
-  const bool xpend = s.S[S_XPEND] != 0.0;
-  const double alpha_prev = xpend ? s.S[S_ALPHA] : 0.0;
-
-  long long off_c = (long long)i_first * plane + own_off;  // own node A in the plane being combined
-  int ipl = i_first;
-
-#define DPP_ISSUE(SL)                                                                                     \
-  {                                                                                                       \
-    const bool in = (unsigned)ipl < (unsigned)ni;                                                         \
-    const bool xin = in && ipl >= i_lo && ipl < i_hi && xpend;                                            \
-    const long long o = off_c + (long long)(ipl - ip) * plane;                                            \
-    _Pragma("unroll") for (int f = 0; f < NF; ++f) {                                                      \
-      const unsigned so = (unsigned)((((SL)*NF + f) * SLOT + own_e) * 8);                                 \
-      cp_async8(sr_base + so, s.r[f] + o, in && ownA_ok);                                                 \
-      cp_async8(sr_base + so + SROW * 8, s.r[f] + o + nk, in && ownB_ok);                                 \
-      cp_async8(sp_base + so, s.pin[f] + o, in && ownA_ok);                                               \
-      cp_async8(sp_base + so + SROW * 8, s.pin[f] + o + nk, in && ownB_ok);                               \
-      if (is_halo) {                                                                                      \
-        const unsigned sh = (unsigned)((((SL)*NF + f) * SLOT + halo_e) * 8);                              \
-        cp_async8(sr_base + sh, s.r[f] + o + halo_delta, in && halo_ok);                                  \
-        cp_async8(sp_base + sh, s.pin[f] + o + halo_delta, in && halo_ok);                                \
-      }                                                                                                   \
-      const unsigned sxo = (unsigned)((((SL)*NF + f) * XSLOT + xown_e) * 8);                              \
-      cp_async8(sx_base + sxo, s.x[f] + o, xin && actA);                                                  \
-      cp_async8(sx_base + sxo + TK * 8, s.x[f] + o + nk, xin && actB);                                    \
-    }                                                                                                     \
-    cp_async_commit();                                                                                    \
-    ++ipl;                                                                                                \
-  }
-
-  const double myo = s.mo[1], mzo = s.mo[2], kyo = s.ko[1], kzo = s.ko[2];
-  const double mCor = myo * mzo, kCor = kyo * mzo + myo * kzo;
-  double mEJ = 0, kEJ = 0;
-  double mEK[2] = {0, 0}, kEK[2] = {0, 0};
-  double mC[2] = {0, 0}, kC[2] = {0, 0};
-  if (k < nk) {
-    const double mzc = __ldg(&s.m1d[2][k * 3 + 1]), kzc = __ldg(&s.k1d[2][k * 3 + 1]);
-    mEJ = myo * mzc;
-    kEJ = kyo * mzc + myo * kzc;
+  const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&sm.mbar[0]);
+  const unsigned sr_base = (unsigned)__cvta_generic_to_shared(&sm.r[0][0]);
+  const unsigned sp_base = (unsigned)__cvta_generic_to_shared(&sm.p[0][0]);
+  const unsigned sx_base = (unsigned)__cvta_generic_to_shared(&sm.x[0][0]);
+  if (tid == 0) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int jr = jA + r;
-      if (jr < nj) {
-        const double myc = __ldg(&s.m1d[1][jr * 3 + 1]), kyc = __ldg(&s.k1d[1][jr * 3 + 1]);
-        mEK[r] = myc * mzo;
-        kEK[r] = kyc * mzo + myc * kzo;
-        mC[r] = myc * mzc;
-        kC[r] = kyc * mzc + myc * kzc;
+    for (int q = 0; q < RING; ++q) mbar_init(mbar0 + 8 * q, 1);
+    fence_mbar_init();
+  }
+  if (tid < 16) sm.dtab[tid] = (FUSED && tid < 8 * NF) ? s.dtab[tid] : 1.0;
+  // scalars of the iteration (device resident; written by the reduction epilogues)
+  double beta = 0.0, alpha_prev = 0.0;
+  bool xpend = false;
+  if (FUSED) {
+    beta = (s.S[S_ITS] == 0.0) ? 0.0 : s.S[S_RZ] / s.S[S_RZ_OLD];
+    xpend = s.S[S_XPEND] != 0.0;
+    alpha_prev = xpend ? s.S[S_ALPHA] : 0.0;
+  }
+  double dot = 0.0;
+  unsigned phase = 0;  // bit q = parity of the next completion of ring slot q
+  const long long plane = s.plane;
+  const int pitch = s.pitch;
+  __syncthreads();
+
+  // Balanced persistent partition: the (tile, plane) steps of the whole grid are cut into gridDim.x equal
+  // contiguous ranges (one CTA each, one wave of 2 CTAs per SM); a range is processed as runs of
+  // consecutive planes of one tile (2 redundant planes per run).
+  const long long total = (long long)s.ntj * s.ntk * nown;
+  long long wbeg = (total * blockIdx.x) / gridDim.x;
+  const long long wend = (total * (blockIdx.x + 1)) / gridDim.x;
+  for (; wbeg < wend;) {
+    const int tile = (int)(wbeg / nown);
+    const int run_a = (int)(wbeg - (long long)tile * nown);
+    const int run_len = (int)((wend - wbeg) < (long long)(nown - run_a) ? (wend - wbeg) : (long long)(nown - run_a));
+    wbeg += run_len;
+    const int i_lo = s.i_begin + run_a, i_hi = i_lo + run_len;
+    const int tkid = tile % s.ntk, tjid = tile / s.ntk;
+    const int nkp = (nk + 1) >> 1;  // tiles are cut between even columns
+    const int k0 = 2 * bstart(tkid, nkp, s.ntk), k1 = min(nk, 2 * bstart(tkid + 1, nkp, s.ntk));
+    const int j0 = bstart(tjid, nj, s.ntj), j1 = bstart(tjid + 1, nj, s.ntj);
+    const int jA = j0 + 2 * ty, jB = jA + 1, k = k0 + tx;
+    const bool actA = (jA < j1) && (k < k1), actB = (jB < j1) && (k < k1);
+    const int i_first = i_lo - 1;
+    // planes whose p this run stores: its output planes, plus the ghost plane next to the first/last owned one
+    const int pw_lo = (i_lo == s.i_begin && s.i_begin > 0) ? i_lo - 1 : i_lo;
+    const int pw_hi = (i_hi == s.i_end && s.i_end < ni) ? i_hi + 1 : i_hi;
+
+    // the elements this thread combines: its two nodes + at most one node of the halo ring
+    constexpr int HW = TK + 2;               // width of the halo ring (nodes k0-1 .. k0+TK)
+    constexpr int HALO = 2 * HW + 2 * TJ;
+    int hr = 0, hc = 0;
+    const bool is_halo = FUSED && tid < HALO;
+    if (is_halo) {
+      if (tid < HW) { hr = 0; hc = tid; }
+      else if (tid < 2 * HW) { hr = TJ + 1; hc = tid - HW; }
+      else if (tid < 2 * HW + TJ) { hr = tid - 2 * HW + 1; hc = 0; }
+      else { hr = tid - 2 * HW - TJ + 1; hc = TK + 1; }
+    }
+    const int jH = j0 - 1 + hr, kH = k0 - 1 + hc;
+    const int own_e = (2 * ty + 1) * SROW + tx + 2;
+    const int halo_e = hr * SROW + hc + 1;
+    const int xown_e = 2 * ty * TK + tx;
+    const int clsA = ((jA == 0 || jA == nj - 1) ? 2 : 0) + ((k == 0 || k == nk - 1) ? 1 : 0);
+    const int clsB = ((jB == 0 || jB == nj - 1) ? 2 : 0) + ((k == 0 || k == nk - 1) ? 1 : 0);
+    const int clsH = ((jH == 0 || jH == nj - 1) ? 2 : 0) + ((kH == 0 || kH == nk - 1) ? 1 : 0);
+
+    long long off_c = (long long)i_first * plane + (long long)jA * pitch + k;  // node A in the plane being combined
+
+    // producer (one thread): fetch plane PL into ring slot SL
+#define DPP_ISSUE(SL, PL)                                                                              \
+  if (tid == 0) {                                                                                      \
+    const bool xin = FUSED && xpend && (PL) >= i_lo && (PL) < i_hi;                                    \
+    const unsigned mb = mbar0 + 8 * (SL);                                                              \
+    fence_proxy_async();                                                                               \
+    mbar_expect_tx(mb, (unsigned)((FUSED ? 2 : 1) * NF * SLOT * 8 + (xin ? NF * XSLOT * 8 : 0)));      \
+    if (FUSED) tma_load_4d(sr_base + (SL)*RS * 8, &tm_r, mb, k0 - 2, j0 - 1, (PL), 0);                 \
+    tma_load_4d(sp_base + (SL)*RS * 8, &tm_p, mb, k0 - 2, j0 - 1, (PL), 0);                            \
+    if (xin) tma_load_4d(sx_base + (SL)*NF * XSLOT * 8, &tm_x, mb, k0, j0, (PL), 0);                   \
+  }
+
+    const double myo = s.mo[1], mzo = s.mo[2], kyo = s.ko[1], kzo = s.ko[2];
+    const double mCor = myo * mzo, kCor = kyo * mzo + myo * kzo;
+    double mEJ = 0, kEJ = 0;
+    double mEK[2] = {0, 0}, kEK[2] = {0, 0};
+    double mC[2] = {0, 0}, kC[2] = {0, 0};
+    if (k < nk) {
+      const double mzc = __ldg(&s.m1d[2][k * 3 + 1]), kzc = __ldg(&s.k1d[2][k * 3 + 1]);
+      mEJ = myo * mzc;
+      kEJ = kyo * mzc + myo * kzc;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int jr = jA + r;
+        if (jr < nj) {
+          const double myc = __ldg(&s.m1d[1][jr * 3 + 1]), kyc = __ldg(&s.k1d[1][jr * 3 + 1]);
+          mEK[r] = myc * mzo;
+          kEK[r] = kyc * mzo + myc * kzo;
+          mC[r] = myc * mzc;
+          kC[r] = kyc * mzc + myc * kzc;
+        }
       }
     }
-  }
-  const double mxo = s.mo[0], kxo = s.ko[0];
+    const double mxo = s.mo[0], kxo = s.ko[0];
 
-  double qc[NF][2][3], qd[NF][2][3], prev_cen[NF][2];
+    double qc[NF][2][3], qd[NF][2][3], prev_cen[NF][2];
 #pragma unroll
-  for (int f = 0; f < NF; ++f)
+    for (int f = 0; f < NF; ++f)
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+      for (int r = 0; r < 2; ++r) {
 #pragma unroll
-      for (int d = 0; d < 3; ++d) qc[f][r][d] = qd[f][r][d] = 0.0;
-      prev_cen[f][r] = 0.0;
+        for (int d = 0; d < 3; ++d) qc[f][r][d] = qd[f][r][d] = 0.0;
+        prev_cen[f][r] = 0.0;
+      }
+    const double* tbase = &sm.p[0][2 * ty * SROW + tx + 1];
+    // interior-plane reciprocal diagonals of the three nodes (boundary planes re-read the table)
+    double dIA[NF], dIB[NF], dIH[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      dIA[f] = sm.dtab[f * 8 + clsA];
+      dIB[f] = sm.dtab[f * 8 + clsB];
+      dIH[f] = sm.dtab[f * 8 + clsH];
     }
-  double dot = 0.0;
-  const double* tbase = &sm.p[0][0][2 * ty * SROW + tx];
 
-  int ip = i_first;
-  __syncthreads();  // dtab visible
-  // interior-plane reciprocal diagonals of the three nodes (boundary planes re-read the table)
-  double dIA[NF], dIB[NF], dIH[NF];
-#pragma unroll
-  for (int f = 0; f < NF; ++f) {
-    dIA[f] = sm.dtab[f * 8 + clsA];
-    dIB[f] = sm.dtab[f * 8 + clsB];
-    dIH[f] = sm.dtab[f * 8 + clsH];
-  }
+    int ip = i_first;
+    __syncthreads();  // the ring is free: every thread finished the previous run
+    DPP_ISSUE(2, i_first)
+    if (i_first + 1 <= i_hi) DPP_ISSUE(0, i_first + 1)
 
-  DPP_ISSUE(2)
-  DPP_ISSUE(0)
-
+  // one plane step: plane ip is in ring slot C; plane ip+2 is fetched into slot B (= slot of plane ip-1)
 #define DPP_STEP(A, B, C)                                                                             \
   {                                                                                                   \
-    cp_async_wait<RING - 2>();                                                                        \
-    const bool pbnd = (ip == 0 && s.dom_lo) || (ip == ni - 1 && s.dom_hi);                            \
-    const bool pwr = ip >= pw_lo && ip < pw_hi;                                                       \
-    const bool xwr = xpend && ip >= i_lo && ip < i_hi;                                                \
+    mbar_wait(mbar0 + 8 * (C), (phase >> (C)) & 1u);                                                  \
+    phase ^= 1u << (C);                                                                               \
     double cen[NF][2];                                                                                \
-    _Pragma("unroll") for (int f = 0; f < NF; ++f) {                                                  \
-      double* sp = &sm.p[C][f][0];                                                                    \
-      const double* sr = &sm.r[C][f][0];                                                              \
-      const double dA = pbnd ? sm.dtab[f * 8 + 4 + clsA] : dIA[f];                                    \
-      const double dB = pbnd ? sm.dtab[f * 8 + 4 + clsB] : dIB[f];                                    \
-      const double poA = sp[own_e], poB = sp[own_e + SROW];                                           \
-      const double pnA = fma(beta, poA, dA * sr[own_e]);                                              \
-      const double pnB = fma(beta, poB, dB * sr[own_e + SROW]);                                       \
-      sp[own_e] = pnA;                                                                                \
-      sp[own_e + SROW] = pnB;                                                                         \
-      if (is_halo) {                                                                                  \
-        const double dH = pbnd ? sm.dtab[f * 8 + 4 + clsH] : dIH[f];                                  \
-        sp[halo_e] = fma(beta, sp[halo_e], dH * sr[halo_e]);                                          \
+    if (FUSED) {                                                                                      \
+      const bool pbnd = (ip == 0 && s.dom_lo) || (ip == ni - 1 && s.dom_hi);                          \
+      const bool pwr = ip >= pw_lo && ip < pw_hi;                                                     \
+      const bool xwr = xpend && ip >= i_lo && ip < i_hi;                                              \
+      _Pragma("unroll") for (int f = 0; f < NF; ++f) {                                                \
+        double* sp = &sm.p[C][f * SLOT];                                                              \
+        const double* sr = &sm.r[C][f * SLOT];                                                        \
+        const double dA = pbnd ? sm.dtab[f * 8 + 4 + clsA] : dIA[f];                                  \
+        const double dB = pbnd ? sm.dtab[f * 8 + 4 + clsB] : dIB[f];                                  \
+        const double poA = sp[own_e], poB = sp[own_e + SROW];                                         \
+        const double pnA = fma(beta, poA, dA * sr[own_e]);                                            \
+        const double pnB = fma(beta, poB, dB * sr[own_e + SROW]);                                     \
+        sp[own_e] = pnA;                                                                              \
+        sp[own_e + SROW] = pnB;                                                                       \
+        if (is_halo) {                                                                                \
+          const double dH = pbnd ? sm.dtab[f * 8 + 4 + clsH] : dIH[f];                                \
+          sp[halo_e] = fma(beta, sp[halo_e], dH * sr[halo_e]);                                        \
+        }                                                                                             \
+        double* po = s.pout + f * s.field + off_c;                                                    \
+        if (pwr) {                                                                                    \
+          if (actA) po[0] = pnA;                                                                      \
+          if (actB) po[pitch] = pnB;                                                                  \
+        }                                                                                             \
+        if (xwr) {                                                                                    \
+          const double* sx = &sm.x[C][f * XSLOT];                                                     \
+          double* xo = s.x + f * s.field + off_c;                                                     \
+          if (actA) xo[0] = fma(alpha_prev, poA, sx[xown_e]);                                         \
+          if (actB) xo[pitch] = fma(alpha_prev, poB, sx[xown_e + TK]);                                \
+        }                                                                                             \
+        cen[f][0] = pnA;                                                                              \
+        cen[f][1] = pnB;                                                                              \
       }                                                                                               \
-      if (pwr) {                                                                                      \
-        if (actA) s.pout[f][off_c] = pnA;                                                             \
-        if (actB) s.pout[f][off_c + nk] = pnB;                                                        \
-      }                                                                                               \
-      if (xwr) {                                                                                      \
-        const double* sx = &sm.x[C][f][0];                                                            \
-        if (actA) s.x[f][off_c] = fma(alpha_prev, poA, sx[xown_e]);                                   \
-        if (actB) s.x[f][off_c + nk] = fma(alpha_prev, poB, sx[xown_e + TK]);                         \
-      }                                                                                               \
-      cen[f][0] = pnA;                                                                                \
-      cen[f][1] = pnB;                                                                                \
     }                                                                                                 \
     __syncthreads();                                                                                  \
-    DPP_ISSUE(B)                                                                                      \
+    if (ip + 2 <= i_hi) DPP_ISSUE(B, ip + 2)                                                          \
     _Pragma("unroll") for (int f = 0; f < NF; ++f) {                                                  \
-      const double* t = tbase + ((C)*NF + f) * SLOT;                                                  \
+      const double* t = tbase + (C)*RS + f * SLOT;                                                    \
       const double e0 = t[0] + t[2], c0 = t[1];                                                       \
       const double e1 = t[SROW] + t[SROW + 2], c1 = t[SROW + 1];                                      \
       const double e2 = t[2 * SROW] + t[2 * SROW + 2], c2 = t[2 * SROW + 1];                          \
       const double e3 = t[3 * SROW] + t[3 * SROW + 2], c3 = t[3 * SROW + 1];                          \
       const double corA = e0 + e2, ejA = c0 + c2, corB = e1 + e3, ejB = c1 + c3;                      \
+      if (!FUSED) {                                                                                   \
+        cen[f][0] = c1;                                                                               \
+        cen[f][1] = c2;                                                                               \
+      }                                                                                               \
       qc[f][0][C] = fma(mCor, corA, fma(mEK[0], e1, fma(mEJ, ejA, mC[0] * c1)));                      \
       qd[f][0][C] = fma(kCor, corA, fma(kEK[0], e1, fma(kEJ, ejA, kC[0] * c1)));                      \
       qc[f][1][C] = fma(mCor, corB, fma(mEK[1], e2, fma(mEJ, ejB, mC[1] * c2)));                      \
@@ -272,7 +315,7 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s) {
           yv = fma(s.c.cM[f][g], Mx[g][r], yv);                                                       \
         }                                                                                             \
         if (r == 0 ? actA : actB) {                                                                   \
-          s.w[f][off_c - plane + r * nk] = yv;                                                        \
+          s.w[f * s.field + off_c - plane + r * pitch] = yv;                                          \
           dot = fma(prev_cen[f][r], yv, dot);                                                         \
         }                                                                                             \
       }                                                                                               \
@@ -284,42 +327,49 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s) {
     off_c += plane;                                                                                   \
   }
 
-  while (true) {
-    DPP_STEP(0, 1, 2)
-    if (++ip > i_hi) break;
-    DPP_STEP(1, 2, 0)
-    if (++ip > i_hi) break;
-    DPP_STEP(2, 0, 1)
-    if (++ip > i_hi) break;
-  }
+    // planes i_first .. i_hi ; outputs i_lo .. i_hi-1
+    while (true) {
+      DPP_STEP(0, 1, 2)
+      if (++ip > i_hi) break;
+      DPP_STEP(1, 2, 0)
+      if (++ip > i_hi) break;
+      DPP_STEP(2, 0, 1)
+      if (++ip > i_hi) break;
+    }
 #undef DPP_STEP
 #undef DPP_ISSUE
-  cp_async_wait<0>();
+    // nothing is in flight here: every fetched plane was consumed, so the per-slot parity bits stay valid
+  }  // runs
 
+  if (s.dot_partials != nullptr) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  if (tx == 0) sm.red[ty] = dot;
-  __syncthreads();
-  if (tid == 0) {
-    double t = 0.0;
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (tx == 0) sm.red[ty] = dot;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < TY; ++w) t += sm.red[w];
-    s.dot_partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+      for (int w = 0; w < TY; ++w) t += sm.red[w];
+      s.dot_partials[blockIdx.x] = t;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// r -= alpha w ; z = dinv .* r (registers only) ; partial <r,z>, <z,z>.   dinv from the class table.
+// r -= alpha w ; z = dinv .* r (registers only) ; partial <r,z>, <z,z>.   Padded layout, dinv from
+// the class table.  Pad columns hold zeros in r and w and therefore stay zero.
 // ---------------------------------------------------------------------------------------------
 struct RArgs {
-  VecLayout L;
+  int nf;
+  long long field;           // padded field stride
+  long long ob, oe;          // owned padded range [i_begin*plane, i_end*plane)
   double* r;
   const double* w;
   const double* S;
   const double* dtab;
   double* partials;
-  unsigned nj, nk, ni;
-  unsigned long long mag_k, mag_j;   // magic multipliers: q / nk = (q * mag_k) >> sh_k   for q < 2^31
+  unsigned nj, nk, ni, pitch;
+  unsigned long long mag_k, mag_j;   // magic multipliers: q / pitch = (q * mag_k) >> sh_k   for q < 2^31
   unsigned sh_k, sh_j;
   int dom_lo, dom_hi;
 };
@@ -348,8 +398,8 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 }
 
 __device__ __forceinline__ int node_class(const RArgs& a, unsigned q) {
-  const unsigned t = (unsigned)(((unsigned long long)q * a.mag_k) >> a.sh_k);   // q / nk
-  const unsigned k = q - t * a.nk;
+  const unsigned t = (unsigned)(((unsigned long long)q * a.mag_k) >> a.sh_k);   // q / pitch
+  const unsigned k = q - t * a.pitch;
   const unsigned i = (unsigned)(((unsigned long long)t * a.mag_j) >> a.sh_j);   // t / nj
   const unsigned j = t - i * a.nj;
   const int bx = ((i == 0 && a.dom_lo) || (i == a.ni - 1 && a.dom_hi)) ? 4 : 0;
@@ -358,42 +408,50 @@ __device__ __forceinline__ int node_class(const RArgs& a, unsigned q) {
   return bx + by + bz;
 }
 
+template <bool INIT>
 __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
   __shared__ double sm[VT / 32];
   __shared__ double tab[16];
-  if (a.S[S_REASON] != 0.0) return;
-  if (threadIdx.x < 16) tab[threadIdx.x] = (threadIdx.x < 8 * a.L.nf) ? a.dtab[threadIdx.x] : 1.0;
+  if (!INIT && a.S[S_REASON] != 0.0) return;
+  if (threadIdx.x < 16) tab[threadIdx.x] = (threadIdx.x < 8 * a.nf) ? a.dtab[threadIdx.x] : 1.0;
   __syncthreads();
-  const double alpha = a.S[S_ALPHA];
-  const long long nown = a.L.oe - a.L.ob;
+  const double alpha = INIT ? 0.0 : a.S[S_ALPHA];
+  const long long nown = a.oe - a.ob;
   const long long per = (nown + gridDim.x - 1) / gridDim.x;
   const long long b = (long long)blockIdx.x * per;
   const long long e = b + per < nown ? b + per : nown;
   const int f = blockIdx.y;
-  const long long base = (long long)f * a.L.stride;
+  double* rf = a.r + (long long)f * a.field;
+  const double* wf = INIT ? nullptr : a.w + (long long)f * a.field;
   const double* tf = tab + f * 8;
   double srz = 0.0, szz = 0.0;
-  long long q = a.L.ob + b + threadIdx.x;
-  const long long qe = a.L.ob + (e > b ? e : b);
+  long long q = a.ob + b + threadIdx.x;
+  const long long qe = a.ob + (e > b ? e : b);
   for (; q + (UNROLL - 1) * VT < qe; q += UNROLL * VT) {
     double rv[UNROLL], wv[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      rv[u] = a.r[base + q + u * VT];
-      wv[u] = a.w[base + q + u * VT];
+      rv[u] = rf[q + u * VT];
+      wv[u] = INIT ? 0.0 : wf[q + u * VT];
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const double rn = fma(-alpha, wv[u], rv[u]);
-      a.r[base + q + u * VT] = rn;
+      double rn = rv[u];
+      if (!INIT) {
+        rn = fma(-alpha, wv[u], rv[u]);
+        rf[q + u * VT] = rn;
+      }
       const double zv = tf[node_class(a, (unsigned)(q + u * VT))] * rn;
       srz = fma(rn, zv, srz);
       szz = fma(zv, zv, szz);
     }
   }
   for (; q < qe; q += VT) {
-    const double rn = fma(-alpha, a.w[base + q], a.r[base + q]);
-    a.r[base + q] = rn;
+    double rn = rf[q];
+    if (!INIT) {
+      rn = fma(-alpha, wf[q], rn);
+      rf[q] = rn;
+    }
     const double zv = tf[node_class(a, (unsigned)q)] * rn;
     srz = fma(rn, zv, srz);
     szz = fma(zv, zv, szz);
@@ -407,43 +465,69 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
   }
 }
 
-// z0 = dinv .* r with the class table (start of the solve: <r,z>, <z,z> of iteration 0)
-__global__ void __launch_bounds__(VT) k_rz_init(const RArgs a) {
-  __shared__ double sm[VT / 32];
-  __shared__ double tab[16];
-  if (threadIdx.x < 16) tab[threadIdx.x] = (threadIdx.x < 8 * a.L.nf) ? a.dtab[threadIdx.x] : 1.0;
-  __syncthreads();
-  const long long nown = a.L.oe - a.L.ob;
-  const long long per = (nown + gridDim.x - 1) / gridDim.x;
-  const long long b = (long long)blockIdx.x * per;
-  const long long e = b + per < nown ? b + per : nown;
+// ---------------------------------------------------------------------------------------------
+// layout conversion (private padded layout <-> the field-blocked lexicographic layout of the C ABI)
+// ---------------------------------------------------------------------------------------------
+struct PadGeom {
+  int nf;
+  long long n_nodes;     // unpadded field stride
+  long long field;       // padded field stride
+  unsigned nj, nk, pitch;
+  unsigned long long mag_k;
+  unsigned sh_k;
+};
+
+// dst_padded[f][row][k] = src[f][row*nk + k]  (pads untouched: they are zero from allocation)
+__global__ void __launch_bounds__(VT) k_pad_copy(PadGeom g, const double* __restrict__ src, double* __restrict__ dst) {
   const int f = blockIdx.y;
-  const long long base = (long long)f * a.L.stride;
-  double srz = 0.0, szz = 0.0;
-  for (long long q = a.L.ob + b + threadIdx.x; q < a.L.ob + e; q += VT) {
-    const double rn = a.r[base + q];
-    const double zv = tab[f * 8 + node_class(a, (unsigned)q)] * rn;
-    srz = fma(rn, zv, srz);
-    szz = fma(zv, zv, szz);
-  }
-  const double t0 = block_sum(srz, sm);
-  const double t1 = block_sum(szz, sm);
-  if (threadIdx.x == 0) {
-    const size_t bb = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-    a.partials[bb * 2] = t0;
-    a.partials[bb * 2 + 1] = t1;
+  for (long long n = (long long)blockIdx.x * VT + threadIdx.x; n < g.n_nodes; n += (long long)gridDim.x * VT) {
+    const unsigned row = (unsigned)(((unsigned long long)(unsigned)n * g.mag_k) >> g.sh_k);  // n / nk
+    const unsigned k = (unsigned)n - row * g.nk;
+    dst[f * g.field + (long long)row * g.pitch + k] = src[f * g.n_nodes + n];
   }
 }
 
-// x += alpha p for the update still pending when the loop stops
-__global__ void __launch_bounds__(VT) k_cg_x_finalize(VecLayout L, double* __restrict__ x, const double* __restrict__ p,
-                                                       const double* __restrict__ S) {
-  if (S[S_XPEND] == 0.0) return;
-  const double alpha = S[S_ALPHA];
-  const long long nown = L.oe - L.ob;
-  const long long base = (long long)blockIdx.y * L.stride + L.ob;
-  for (long long q = (long long)blockIdx.x * VT + threadIdx.x; q < nown; q += (long long)gridDim.x * VT)
-    x[base + q] = fma(alpha, p[base + q], x[base + q]);
+// x_unpadded = x_padded (+ alpha p_padded when an update is still pending)
+__global__ void __launch_bounds__(VT) k_cg_x_finalize(PadGeom g, const double* __restrict__ xp, const double* __restrict__ pp,
+                                                       const double* __restrict__ S, long long ob, long long oe,
+                                                       double* __restrict__ x) {
+  const double alpha = (S[S_XPEND] != 0.0) ? S[S_ALPHA] : 0.0;
+  const int f = blockIdx.y;
+  for (long long n = ob + (long long)blockIdx.x * VT + threadIdx.x; n < oe; n += (long long)gridDim.x * VT) {
+    const unsigned row = (unsigned)(((unsigned long long)(unsigned)n * g.mag_k) >> g.sh_k);
+    const unsigned k = (unsigned)n - row * g.nk;
+    const long long q = f * g.field + (long long)row * g.pitch + k;
+    x[f * g.n_nodes + n] = fma(alpha, pp[q], xp[q]);
+  }
+}
+
+// node id -> padded offset (row elimination list)
+__global__ void k_pad_ids(long long n, const int32_t* __restrict__ nodes, PadGeom g, int32_t* __restrict__ out) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const unsigned node = (unsigned)nodes[t];
+    const unsigned row = (unsigned)(((unsigned long long)node * g.mag_k) >> g.sh_k);
+    out[t] = (int32_t)((long long)row * g.pitch + (node - row * g.nk));
+  }
+}
+
+struct FixPArgs {
+  const int32_t* ids[2];
+  long long count[2];
+  double* w;
+  const double* p;
+  long long field, ob, oe;
+  int identity;
+  const double* skip_flag;
+};
+
+__global__ void k_fix_rows_padded(const FixPArgs a) {
+  if (a.skip_flag != nullptr && *a.skip_flag != 0.0) return;
+  const long long total = a.count[0] + a.count[1];
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int f = t < a.count[0] ? 0 : 1;
+    const long long q = a.ids[f][f ? t - a.count[0] : t];
+    if (q >= a.ob && q < a.oe) a.w[f * a.field + q] = a.identity ? a.p[f * a.field + q] : 0.0;
+  }
 }
 
 // reciprocal diagonal per boundary class; same expression as k_diag_structured (apply_structured.cu)
@@ -470,7 +554,7 @@ __global__ void k_dinv_table(GridDesc g, Coef c, int nf, int jacobi, double* __r
 }
 
 void magic_div(unsigned d, unsigned long long* mag, unsigned* sh) {
-  // exact floor(q / d) for all q < 2^31 (proof in DESIGN.md): k = 32 + ceil(log2 d), mag = ceil(2^k / d)
+  // exact floor(q / d) for all q < 2^31: k = 32 + ceil(log2 d), mag = ceil(2^k / d)  
   unsigned l = 0;
   while ((1ull << l) < d) ++l;
   const unsigned k = 32 + l;
@@ -478,31 +562,189 @@ void magic_div(unsigned d, unsigned long long* mag, unsigned* sh) {
   *mag = (unsigned long long)((((unsigned __int128)1 << k) + d - 1) / d);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 }  // namespace
+
+// state of the fused path kept per handle
+struct FusedState {
+  int ni = 0, nj = 0, nk = 0, pitch = 0;
+  long long plane = 0, field = 0;
+  double* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // r, p0, p1, w, x  (2 * field doubles each)
+  CUtensorMap tm[2][4];   // [nf-1][r, p0, p1, x]
+  int32_t* bc_pad[2] = {nullptr, nullptr};
+  long long bc_count[2] = {0, 0};
+  int64_t bc_gen[2] = {-1, -1};   // ctx->bc_gen the padded ids were derived from
+  bool attr_set = false;
+};
+
+void cg_fused_destroy(dpp_context* ctx) {
+  FusedState* F = ctx->fused;
+  if (!F) return;
+  for (double* b : F->buf)
+    if (b) cudaFree(b);
+  for (int32_t* b : F->bc_pad)
+    if (b) cudaFree(b);
+  delete F;
+  ctx->fused = nullptr;
+}
 
 bool cg_fused_available(const dpp_context* ctx, int nf, int operator_mode, int pc_type) {
   return ctx->family == DPP_KERNEL_STRUCTURED && ctx->grid.band == 1 && ctx->grid_uniform && !ctx->force_table_kernel &&
          operator_mode == DPP_OP_MATRIX_FREE && (pc_type == DPP_PC_NONE || pc_type == DPP_PC_JACOBI) &&
-         (nf == 1 || nf == 2) && getenv("DPP_NO_FUSED_CG") == nullptr;
+         (nf == 1 || nf == 2) && getenv("DPP_NO_FUSED_CG") == nullptr && encode_fn() != nullptr;
 }
 
-static int make_rargs(dpp_context* ctx, const VecLayout& L, double* r, const double* w, int slot, const double* dtab,
-                      RArgs* out) {
+static PadGeom pad_geom(const dpp_context* ctx, const FusedState* F, int nf) {
+  PadGeom g{};
+  g.nf = nf;
+  g.n_nodes = ctx->n_nodes;
+  g.field = F->field;
+  g.nj = (unsigned)F->nj; g.nk = (unsigned)F->nk; g.pitch = (unsigned)F->pitch;
+  magic_div(g.nk, &g.mag_k, &g.sh_k);
+  return g;
+}
+
+static int make_map(dpp_context* ctx, FusedState* F, CUtensorMap* m, double* base, int nf, bool halo) {
+  const cuuint64_t dims[4] = {(cuuint64_t)F->nk, (cuuint64_t)F->nj, (cuuint64_t)F->ni, (cuuint64_t)nf};
+  const cuuint64_t strides[3] = {(cuuint64_t)F->pitch * 8, (cuuint64_t)F->plane * 8, (cuuint64_t)F->field * 8};
+  const cuuint32_t box[4] = {(cuuint32_t)(halo ? SROW : TK), (cuuint32_t)(halo ? TJ + 2 : TJ), 1u, (cuuint32_t)nf};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult rc = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    ctx->set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
+    return DPP_ERR_CUDA;
+  }
+  return DPP_OK;
+}
+
+// allocate the padded vectors and tensor maps (once per handle / mesh)
+static int fused_state(dpp_context* ctx, FusedState** out) {
+  if (!ctx->fused) {
+    FusedState* F = new FusedState();
+    ctx->fused = F;
+    const GridDesc& g = ctx->grid;
+    F->ni = g.n[0]; F->nj = g.n[1]; F->nk = g.n[2];
+    F->pitch = ((F->nk + 15) / 16) * 16;
+    F->plane = (long long)F->nj * F->pitch;
+    F->field = (long long)F->ni * F->plane;
+    if (F->field >= (1LL << 31)) {
+      ctx->set_error("fused CG: padded field exceeds int32 indexing");
+      return DPP_ERR_INVALID;
+    }
+    for (double*& b : F->buf) {
+      DPP_CHECK(dev_alloc(ctx, &b, 2 * F->field));
+      DPP_CUDA(cudaMemsetAsync(b, 0, sizeof(double) * 2 * F->field, ctx->stream));
+    }
+    for (int nf = 1; nf <= 2; ++nf) {
+      DPP_CHECK(make_map(ctx, F, &F->tm[nf - 1][0], F->buf[0], nf, true));
+      DPP_CHECK(make_map(ctx, F, &F->tm[nf - 1][1], F->buf[1], nf, true));
+      DPP_CHECK(make_map(ctx, F, &F->tm[nf - 1][2], F->buf[2], nf, true));
+      DPP_CHECK(make_map(ctx, F, &F->tm[nf - 1][3], F->buf[4], nf, false));
+    }
+  }
+  *out = ctx->fused;
+  return DPP_OK;
+}
+
+static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, const Coef& c, int pin_idx, double* pout,
+                        int slot, const double* dtab, bool want_dot, int* n_partial_blocks) {
   const GridDesc& g = ctx->grid;
+  const long long uplane = (long long)g.n[1] * g.n[2];
+  if (ctx->owned_begin % uplane || ctx->owned_end % uplane) {
+    ctx->set_error("fused CG: owned range must consist of whole x-planes");
+    return DPP_ERR_INVALID;
+  }
+  FArgs s{};
+  for (int d = 0; d < 3; ++d) {
+    s.n[d] = g.n[d]; s.m1d[d] = g.m1d[d]; s.k1d[d] = g.k1d[d];
+    s.mo[d] = ctx->uni_m_off[d]; s.ko[d] = ctx->uni_k_off[d];
+  }
+  s.pitch = F->pitch; s.plane = F->plane; s.field = F->field;
+  s.mxc_i = ctx->uni_mxc[0]; s.mxc_b = ctx->uni_mxc[1];
+  s.kxc_i = ctx->uni_kxc[0]; s.kxc_b = ctx->uni_kxc[1];
+  s.pout = pout; s.x = F->buf[4]; s.w = F->buf[3];
+  s.c = c;
+  s.dot_partials = want_dot ? ctx->d_partials : nullptr;
+  s.i_begin = (int)(ctx->owned_begin / uplane);
+  s.i_end = (int)(ctx->owned_end / uplane);
+  s.S = fused ? ctx->d_scalars + (size_t)slot * S_SLOT_SIZE : nullptr;
+  s.dtab = dtab;
+  s.dom_lo = ctx->dom_lo; s.dom_hi = ctx->dom_hi;
+  s.ntk = ((g.n[2] + 1) / 2 + TK / 2 - 1) / (TK / 2);   // tiles hold <= TK/2 column pairs
+  s.ntj = (g.n[1] + TJ - 1) / TJ;
+  const int tiles = s.ntk * s.ntj;
+  const int nown = s.i_end - s.i_begin;
+  if (nown <= 0) { *n_partial_blocks = 0; return DPP_OK; }
+  // one wave of persistent CTAs (2 per SM), each with an equal share of the (tile, plane) steps; small
+  // grids get fewer CTAs so that a run stays >= ~8 planes (2 redundant planes per run)
+  const long long total = (long long)tiles * nown;
+  const int nctas = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count * 2, total / 8));
+  if (!F->attr_set) {
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<2>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<2>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
+    F->attr_set = true;
+  }
+  dim3 grid(nctas), block(TK, TY);
+  const CUtensorMap* T = F->tm[nf - 1];
+  if (nf == 2) {
+    if (fused) k_cg_fused_apply<2, true><<<grid, block, sizeof(Smem<2>), ctx->stream>>>(s, T[0], T[pin_idx], T[3]);
+    else k_cg_fused_apply<2, false><<<grid, block, sizeof(Smem<2>), ctx->stream>>>(s, T[0], T[pin_idx], T[3]);
+  } else {
+    if (fused) k_cg_fused_apply<1, true><<<grid, block, sizeof(Smem<1>), ctx->stream>>>(s, T[0], T[pin_idx], T[3]);
+    else k_cg_fused_apply<1, false><<<grid, block, sizeof(Smem<1>), ctx->stream>>>(s, T[0], T[pin_idx], T[3]);
+  }
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  *n_partial_blocks = nctas;
+  return DPP_OK;
+}
+
+static int make_rargs(dpp_context* ctx, FusedState* F, int nf, int slot, const double* dtab, RArgs* out) {
+  const GridDesc& g = ctx->grid;
+  const long long uplane = (long long)g.n[1] * g.n[2];
   RArgs a{};
-  a.L = L;
-  a.r = r;
-  a.w = w;
+  a.nf = nf;
+  a.field = F->field;
+  a.ob = (ctx->owned_begin / uplane) * F->plane;
+  a.oe = (ctx->owned_end / uplane) * F->plane;
+  a.r = F->buf[0];
+  a.w = F->buf[3];
   a.S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
   a.dtab = dtab;
   a.partials = ctx->d_partials;
-  a.ni = (unsigned)g.n[0]; a.nj = (unsigned)g.n[1]; a.nk = (unsigned)g.n[2];
-  magic_div(a.nk, &a.mag_k, &a.sh_k);
+  a.ni = (unsigned)g.n[0]; a.nj = (unsigned)g.n[1]; a.nk = (unsigned)g.n[2]; a.pitch = (unsigned)F->pitch;
+  magic_div(a.pitch, &a.mag_k, &a.sh_k);
   magic_div(a.nj, &a.mag_j, &a.sh_j);
   a.dom_lo = ctx->dom_lo;
   a.dom_hi = ctx->dom_hi;
   *out = a;
   return DPP_OK;
+}
+
+static int r_blocks(const dpp_context* ctx, const RArgs& a) {
+  const long long nown = a.oe - a.ob;
+  long long want = (nown + (long long)VT * UNROLL * 4 - 1) / ((long long)VT * UNROLL * 4);
+  const long long cap = std::max(1, (ctx->sm_count * 8) / std::max(1, a.nf));
+  return (int)std::max(1LL, std::min(std::min(want, cap), (long long)kMaxPartialBlocks / 2));
 }
 
 int cg_fused_table(dpp_context* ctx, const Coef& c, int nf, int pc_type, double* d_tab) {
@@ -512,95 +754,138 @@ int cg_fused_table(dpp_context* ctx, const Coef& c, int nf, int pc_type, double*
   return DPP_OK;
 }
 
-int cg_fused_rz_init(dpp_context* ctx, const VecLayout& L, const double* r, int slot, const double* dtab, int* nblocks) {
+// start of a solve: r_padded = b, p = 0, x = 0; partial <r,z>, <z,z>
+int cg_fused_begin(dpp_context* ctx, int nf, const double* b) {
+  FusedState* F = nullptr;
+  DPP_CHECK(fused_state(ctx, &F));
+  const PadGeom g = pad_geom(ctx, F, nf);
+  for (int v : {1, 2, 4})
+    for (int f = 0; f < nf; ++f)
+      DPP_CUDA(cudaMemsetAsync(F->buf[v] + f * F->field, 0, sizeof(double) * F->field, ctx->stream));
+  dim3 grid((unsigned)std::min<long long>((ctx->n_nodes + VT - 1) / VT, (long long)ctx->sm_count * 16), nf);
+  k_pad_copy<<<grid, VT, 0, ctx->stream>>>(g, b, F->buf[0]);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+
+int cg_fused_rz_init(dpp_context* ctx, int nf, int slot, const double* dtab, int* nblocks) {
+  FusedState* F = nullptr;
+  DPP_CHECK(fused_state(ctx, &F));
   RArgs a{};
-  DPP_CHECK(make_rargs(ctx, L, const_cast<double*>(r), nullptr, slot, dtab, &a));
-  dim3 grid(vec_launch_blocks(ctx, L), L.nf);
-  k_rz_init<<<grid, VT, 0, ctx->stream>>>(a);
+  DPP_CHECK(make_rargs(ctx, F, nf, slot, dtab, &a));
+  dim3 grid(r_blocks(ctx, a), nf);
+  k_cg_r_update<true><<<grid, VT, 0, ctx->stream>>>(a);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   *nblocks = grid.x * grid.y;
   return DPP_OK;
 }
 
-int cg_fused_r_update(dpp_context* ctx, const VecLayout& L, double* r, const double* w, int slot, const double* dtab,
-                      int* nblocks) {
+int cg_fused_r_update(dpp_context* ctx, int nf, int slot, const double* dtab, int* nblocks) {
+  FusedState* F = nullptr;
+  DPP_CHECK(fused_state(ctx, &F));
   RArgs a{};
-  DPP_CHECK(make_rargs(ctx, L, r, w, slot, dtab, &a));
-  dim3 grid(vec_launch_blocks(ctx, L), L.nf);
-  k_cg_r_update<<<grid, VT, 0, ctx->stream>>>(a);
+  DPP_CHECK(make_rargs(ctx, F, nf, slot, dtab, &a));
+  dim3 grid(r_blocks(ctx, a), nf);
+  k_cg_r_update<false><<<grid, VT, 0, ctx->stream>>>(a);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   *nblocks = grid.x * grid.y;
   return DPP_OK;
 }
 
-int cg_fused_x_finalize(dpp_context* ctx, const VecLayout& L, double* x, const double* p, int slot) {
-  dim3 grid(vec_launch_blocks(ctx, L), L.nf);
-  k_cg_x_finalize<<<grid, VT, 0, ctx->stream>>>(L, x, p, ctx->d_scalars + (size_t)slot * S_SLOT_SIZE);
-  ctx->launches++;
-  DPP_CUDA(cudaGetLastError());
-  return DPP_OK;
-}
-
-// w = A p with p = dinv.*r + beta*pin formed on chip; pout = p; x += alpha_prev * pin; partial <p,w>
-int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, const double* const* r, const double* const* pin,
-                   double* const* pout, double* const* x, double* const* w, int slot, const double* dtab,
+// iteration `it` (0-based count of applies so far): w = A p, p = dinv.*r + beta*p_prev, x += alpha_prev p_prev
+int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const int* fld, int slot, const double* dtab,
                    int* n_partial_blocks) {
-  const GridDesc& g = ctx->grid;
-  const long long plane = (long long)g.n[1] * g.n[2];
-  if (ctx->owned_begin % plane || ctx->owned_end % plane) {
-    ctx->set_error("fused CG: owned range must consist of whole x-planes");
-    return DPP_ERR_INVALID;
-  }
-  FArgs s{};
-  for (int d = 0; d < 3; ++d) {
-    s.n[d] = g.n[d]; s.m1d[d] = g.m1d[d]; s.k1d[d] = g.k1d[d];
-    s.mo[d] = ctx->uni_m_off[d]; s.ko[d] = ctx->uni_k_off[d];
-  }
-  s.mxc_i = ctx->uni_mxc[0]; s.mxc_b = ctx->uni_mxc[1];
-  s.kxc_i = ctx->uni_kxc[0]; s.kxc_b = ctx->uni_kxc[1];
-  for (int f = 0; f < nf; ++f) { s.r[f] = r[f]; s.pin[f] = pin[f]; s.pout[f] = pout[f]; s.x[f] = x[f]; s.w[f] = w[f]; }
-  s.c = c;
-  s.dot_partials = ctx->d_partials;
-  s.i_begin = (int)(ctx->owned_begin / plane);
-  s.i_end = (int)(ctx->owned_end / plane);
-  s.S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
-  s.dtab = dtab;
-  s.dom_lo = ctx->dom_lo;
-  s.dom_hi = ctx->dom_hi;
-  s.ntk = (g.n[2] + TK - 1) / TK;
-  s.ntj = (g.n[1] + TJ - 1) / TJ;
-  const int tiles = s.ntk * s.ntj;
-  const int nown = s.i_end - s.i_begin;
-  if (nown <= 0) { *n_partial_blocks = 0; return DPP_OK; }
-  const int capacity = ctx->sm_count * 2;
-  int nseg = (2 * capacity + tiles / 2) / tiles;
-  nseg = std::max(1, std::min(nseg, std::max(1, nown / 8)));
-  while ((long long)tiles * nseg > kMaxPartialBlocks && nseg > 1) --nseg;
-  if ((long long)tiles * nseg > kMaxPartialBlocks * (long long)kMaxDotWidth) {
-    ctx->set_error("fused CG: too many tiles for the reduction scratch");
-    return DPP_ERR_INVALID;
-  }
-  s.nseg = nseg;
-  dim3 grid(tiles, nseg), block(TK, TY);
-  static bool attr_set[2] = {false, false};
-  if (nf == 2) {
-    if (!attr_set[1]) {
-      DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<2>)));
-      attr_set[1] = true;
+  FusedState* F = nullptr;
+  DPP_CHECK(fused_state(ctx, &F));
+  const int pin = 1 + (int)(it & 1), pout = 1 + (int)((it + 1) & 1);
+  DPP_CHECK(launch_apply(ctx, F, nf, true, c, pin, F->buf[pout], slot, dtab, true, n_partial_blocks));
+  // row elimination: w = p on constrained rows (identity rows of A_bc)
+  const PadGeom g = pad_geom(ctx, F, nf);
+  FixPArgs fx{};
+  for (int f = 0; f < nf; ++f) {
+    const int fl = fld[f];
+    if (F->bc_gen[fl] != ctx->bc_gen[fl]) {
+      if (F->bc_pad[fl]) cudaFree(F->bc_pad[fl]);
+      F->bc_pad[fl] = nullptr;
+      F->bc_count[fl] = ctx->n_bc[fl];
+      F->bc_gen[fl] = ctx->bc_gen[fl];
+      if (ctx->n_bc[fl] > 0) {
+        DPP_CHECK(dev_alloc(ctx, &F->bc_pad[fl], ctx->n_bc[fl]));
+        const int blocks = (int)std::min<long long>((ctx->n_bc[fl] + 255) / 256, 4096);
+        k_pad_ids<<<blocks, 256, 0, ctx->stream>>>(ctx->n_bc[fl], ctx->d_bc_nodes[fl], g, F->bc_pad[fl]);
+        ctx->launches++;
+      }
     }
-    k_cg_fused_apply<2><<<grid, block, sizeof(Smem<2>), ctx->stream>>>(s);
-  } else {
-    if (!attr_set[0]) {
-      DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
-      attr_set[0] = true;
-    }
-    k_cg_fused_apply<1><<<grid, block, sizeof(Smem<1>), ctx->stream>>>(s);
+    fx.ids[f] = F->bc_pad[fl];
+    fx.count[f] = F->bc_count[fl];
   }
+  const long long total = fx.count[0] + fx.count[1];
+  if (total > 0) {
+    const long long uplane = (long long)ctx->grid.n[1] * ctx->grid.n[2];
+    fx.w = F->buf[3];
+    fx.p = F->buf[pout];
+    fx.field = F->field;
+    fx.ob = (ctx->owned_begin / uplane) * F->plane;
+    fx.oe = (ctx->owned_end / uplane) * F->plane;
+    fx.identity = 1;
+    fx.skip_flag = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE + S_REASON;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 8));
+    k_fix_rows_padded<<<blocks, 256, 0, ctx->stream>>>(fx);
+    ctx->launches++;
+  }
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+
+// x (unpadded, owned rows) = x_padded + pending alpha * p, with p the direction of the last executed apply
+int cg_fused_x_finalize(dpp_context* ctx, int nf, long long its, int slot, double* x) {
+  FusedState* F = nullptr;
+  DPP_CHECK(fused_state(ctx, &F));
+  const PadGeom g = pad_geom(ctx, F, nf);
+  const long long nown = ctx->owned_end - ctx->owned_begin;
+  dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((nown + VT - 1) / VT, (long long)ctx->sm_count * 16)), nf);
+  k_cg_x_finalize<<<grid, VT, 0, ctx->stream>>>(g, F->buf[4], F->buf[1 + (int)(its & 1)],
+                                                ctx->d_scalars + (size_t)slot * S_SLOT_SIZE, ctx->owned_begin,
+                                                ctx->owned_end, x);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
-  *n_partial_blocks = tiles * nseg;
+  return DPP_OK;
+}
+
+// ghost planes of r (padded layout) for slab-partitioned runs
+int cg_fused_halo_r(dpp_context* ctx, int nf) {
+  if (ctx->world <= 1) return DPP_OK;
+  FusedState* F = nullptr;
+  DPP_CHECK(fused_state(ctx, &F));
+  const long long uplane = (long long)ctx->grid.n[1] * ctx->grid.n[2];
+  return comm_halo_planes(ctx, F->buf[0], nf, F->field, F->plane, (int)(ctx->owned_begin / uplane),
+                          (int)(ctx->owned_end / uplane));
+}
+
+// measurement: fill the padded work vectors with pseudo-random data (zero on constrained rows and pads)
+int cg_fused_plain_apply(dpp_context* ctx, int nf, const Coef& c, bool want_dot, int* n_partial_blocks) {
+  FusedState* F = nullptr;
+  DPP_CHECK(fused_state(ctx, &F));
+  return launch_apply(ctx, F, nf, false, c, 1, nullptr, 0, ctx->d_dtab, want_dot, n_partial_blocks);
+}
+
+double* cg_fused_buffer(dpp_context* ctx, int which) {
+  FusedState* F = nullptr;
+  if (fused_state(ctx, &F) != DPP_OK) return nullptr;
+  return F->buf[which];
+}
+
+int cg_fused_pad_from(dpp_context* ctx, int which, const double* src) {
+  FusedState* F = nullptr;
+  DPP_CHECK(fused_state(ctx, &F));
+  const PadGeom g = pad_geom(ctx, F, 2);
+  dim3 grid((unsigned)std::min<long long>((ctx->n_nodes + VT - 1) / VT, (long long)ctx->sm_count * 16), 2);
+  k_pad_copy<<<grid, VT, 0, ctx->stream>>>(g, src, F->buf[which]);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
   return DPP_OK;
 }
 

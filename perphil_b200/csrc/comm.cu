@@ -146,6 +146,27 @@ int comm_halo_exchange(dpp_context* ctx, double* const* fields, int nf) {
   return DPP_OK;
 }
 
+int comm_halo_planes(dpp_context* ctx, double* base, int nf, long long field_stride, long long plane_elems, int i_begin,
+                     int i_end) {
+  Comm* C = ctx->comm;
+  if (!C || ctx->world <= 1) return DPP_OK;
+  DPP_NCCL(nccl().GroupStart());
+  for (Neighbor& nb : C->nbrs) {
+    const bool lower = nb.peer < ctx->rank;
+    if (lower ? i_begin <= 0 : false) continue;
+    // lower neighbour: send my first owned plane, receive my lower ghost plane; upper: last owned / upper ghost
+    const long long send_pl = lower ? i_begin : i_end - 1;
+    const long long recv_pl = lower ? i_begin - 1 : i_end;
+    for (int f = 0; f < nf; ++f) {
+      double* fb = base + f * field_stride;
+      DPP_NCCL(nccl().Send(fb + send_pl * plane_elems, (size_t)plane_elems, ncclDouble, nb.peer, C->comm, ctx->stream));
+      DPP_NCCL(nccl().Recv(fb + recv_pl * plane_elems, (size_t)plane_elems, ncclDouble, nb.peer, C->comm, ctx->stream));
+    }
+  }
+  DPP_NCCL(nccl().GroupEnd());
+  return DPP_OK;
+}
+
 int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n) {
   Comm* C = ctx->comm;
   if (!C || ctx->world <= 1) return DPP_OK;

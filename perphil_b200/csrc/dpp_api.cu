@@ -118,6 +118,7 @@ void dpp_destroy(dpp_handle ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   dpp::krylov_destroy(ctx);
+  dpp::cg_fused_destroy(ctx);
   dpp::csr_destroy(ctx);
   dpp::comm_destroy(ctx);
   void* ptrs[] = {ctx->d_cnm, ctx->d_coords, ctx->ccnm_alias ? nullptr : ctx->d_ccnm, ctx->d_tables, ctx->d_adj_ptr,
@@ -222,6 +223,7 @@ int dpp_set_dirichlet(dpp_handle ctx, int field, int64_t n, const int32_t* nodes
     ctx->d_bc_nodes[field] = nullptr;
   }
   ctx->n_bc[field] = n;
+  ctx->bc_gen[field]++;
   ctx->have_bc[field] = n > 0;
   ctx->invalidate();
   dpp::csr_invalidate(ctx);
@@ -375,10 +377,10 @@ int dpp_time_apply(dpp_handle ctx, int mode, int warmup, int reps, int with_dot,
   return DPP_OK;
 }
 
-int dpp_time_cg_kernels(dpp_handle ctx, int warmup, int reps, double* apply_ms, double* update_ms) {
-  if (!ctx || reps <= 0 || warmup < 0 || !apply_ms || !update_ms) return DPP_ERR_INVALID;
+int dpp_time_cg_kernels(dpp_handle ctx, int warmup, int reps, double* apply_ms, double* update_ms, double* matvec_ms) {
+  if (!ctx || reps <= 0 || warmup < 0 || !apply_ms || !update_ms || !matvec_ms) return DPP_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  return dpp::krylov_time_cg_kernels(ctx, warmup, reps, apply_ms, update_ms);
+  return dpp::krylov_time_cg_kernels(ctx, warmup, reps, apply_ms, update_ms, matvec_ms);
 }
 
 int dpp_host_alloc(void** ptr, int64_t bytes) {

@@ -61,6 +61,7 @@ struct GridDesc {
 };
 
 struct Krylov;  // krylov.cu
+struct FusedState;  // cg_fused_uniform.cu
 struct CsrMatrix;
 struct Comm;
 
@@ -112,6 +113,7 @@ struct dpp_context {
   bool have_bc[2] = {false, false};
   int32_t* d_bc_nodes[2] = {nullptr, nullptr};  // constrained node ids per field
   int64_t n_bc[2] = {0, 0};
+  int64_t bc_gen[2] = {0, 0};     // bumped by every dpp_set_dirichlet of that field
 
   // partition
   int rank = 0, world = 1;
@@ -121,6 +123,7 @@ struct dpp_context {
 
   // work vectors / solver state (krylov.cu)
   dpp::Krylov* krylov = nullptr;
+  dpp::FusedState* fused = nullptr;  // padded vectors + TMA descriptors of the fused CG path
   dpp::CsrMatrix* csr = nullptr;
   double* d_solution = nullptr;   // [2*n_nodes]
   double* d_diag = nullptr;       // [2*n_nodes] diag(A_bc), valid when diag_valid
@@ -174,6 +177,10 @@ int vec_copy(dpp_context* ctx, double* dst, const double* src, int64_t n);
 // ---- comm.cu
 int comm_halo_exchange(dpp_context* ctx, double* const* fields, int nf);
 int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n);
+// ghost x-planes of a plane-contiguous (padded) vector: owned boundary planes -> the slab neighbours
+int comm_halo_planes(dpp_context* ctx, double* base, int nf, long long field_stride, long long plane_elems, int i_begin,
+                     int i_end);
+void cg_fused_destroy(dpp_context* ctx);
 void comm_destroy(dpp_context* ctx);
 
 // ---- assemble_csr.cu
@@ -189,7 +196,8 @@ void csr_destroy(dpp_context* ctx);
 int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_result* res,
                  double* hist_host, int32_t hist_cap);
 void krylov_destroy(dpp_context* ctx);
-int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply_ms, double* update_ms);
+int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply_ms, double* update_ms,
+                           double* matvec_ms);
 
 template <typename T>
 inline int dev_alloc(dpp_context* ctx, T** p, int64_t count) {

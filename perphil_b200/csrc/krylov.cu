@@ -160,16 +160,13 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
   const double* h = ctx->h_scalars + (size_t)slot * S_SLOT_SIZE;
   if (fused && cg_fused_available(ctx, op.nf, op.mode, pc.type)) {
     // two kernels per iteration (cg_fused_uniform.cu): p, x updates live inside the apply kernel
-    const int64_t n = ctx->n_nodes;
     const Coef coef = op.nf == 2 ? dpp_coef(ctx) : block_coef(ctx, op.row, op.col);
     double* dtab = ctx->d_dtab + (size_t)slot * 16;
-    double* P[2] = {wk.p, wk.z};
     DPP_CHECK(cg_fused_table(ctx, coef, op.nf, pc.type, dtab));
-    DPP_CHECK(vec_zero(ctx, P[0], len));
-    DPP_CHECK(vec_zero(ctx, P[1], len));
-    DPP_CHECK(halo(ctx, wk.r, op.nf));
+    DPP_CHECK(cg_fused_begin(ctx, op.nf, b));
+    DPP_CHECK(cg_fused_halo_r(ctx, op.nf));
     int nb = 0;
-    DPP_CHECK(cg_fused_rz_init(ctx, L, wk.r, slot, dtab, &nb));
+    DPP_CHECK(cg_fused_rz_init(ctx, op.nf, slot, dtab, &nb));
     DPP_CHECK(reduce_partials(ctx, nb, 2, slot, POST_CG_INIT));
     DPP_CHECK(scalars_fetch(ctx, slot));
     const int fld[2] = {op.nf == 2 ? 0 : op.row, 1};
@@ -177,22 +174,16 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
     long long kk = 0;
     while (h[S_REASON] == 0.0) {
       for (int k = 0; k < every; ++k, ++kk) {
-        const double* pin[2] = {P[kk & 1], P[kk & 1] + n};
-        double* pout[2] = {P[(kk + 1) & 1], P[(kk + 1) & 1] + n};
-        const double* rr[2] = {wk.r, wk.r + n};
-        double* xx[2] = {x, x + n};
-        double* ww[2] = {wk.w, wk.w + n};
-        DPP_CHECK(cg_fused_apply(ctx, op.nf, coef, rr, pin, pout, xx, ww, slot, dtab, &nb));
+        DPP_CHECK(cg_fused_apply(ctx, op.nf, coef, kk, fld, slot, dtab, &nb));
         ctx->krylov->apply_count++;
-        DPP_CHECK(structured_fix_rows(ctx, op.nf, fld, ww, pout, 1, S + S_REASON));
         DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
-        DPP_CHECK(cg_fused_r_update(ctx, L, wk.r, wk.w, slot, dtab, &nb));
+        DPP_CHECK(cg_fused_r_update(ctx, op.nf, slot, dtab, &nb));
         DPP_CHECK(reduce_partials(ctx, nb, 2, slot, POST_CG_RZ));
-        DPP_CHECK(halo(ctx, wk.r, op.nf));
+        DPP_CHECK(cg_fused_halo_r(ctx, op.nf));
       }
       DPP_CHECK(scalars_fetch(ctx, slot));
     }
-    DPP_CHECK(cg_fused_x_finalize(ctx, L, x, P[(long long)h[S_ITS] & 1], slot));
+    DPP_CHECK(cg_fused_x_finalize(ctx, op.nf, (long long)h[S_ITS], slot, x));
     out->its = (int)h[S_ITS];
     out->reason = (int)h[S_REASON];
     out->rnorm = h[S_RNORM];
@@ -546,7 +537,8 @@ __global__ void k_fill_work(long long n, double* __restrict__ x, const uint8_t* 
   }
 }
 
-int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply_ms, double* update_ms) {
+int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply_ms, double* update_ms,
+                           double* matvec_ms) {
   if (!ctx->have_params) {
     ctx->set_error("dpp_time_cg_kernels: call dpp_set_params first");
     return DPP_ERR_STATE;
@@ -558,13 +550,14 @@ int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply
   DPP_CHECK(ensure_work(ctx));
   Krylov* K = ctx->krylov;
   const int64_t n = ctx->n_nodes;
-  const VecLayout L = layout(ctx, 2);
   const int slot = 0;
   double* S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
-  double* vs[4] = {K->r, K->p, K->z, K->x};
+  // pseudo-random work vectors (zero on constrained rows, like every Krylov vector): r, p0, p1, x
+  const int which[4] = {0, 1, 2, 4};
   for (int v = 0; v < 4; ++v) {
-    k_fill_work<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(2 * n, vs[v], ctx->d_mask, 7919ull * (v + 1));
+    k_fill_work<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(2 * n, K->t, ctx->d_mask, 7919ull * (v + 1));
     ctx->launches++;
+    DPP_CHECK(cg_fused_pad_from(ctx, which[v], K->t));
   }
   DPP_CHECK(scalars_init(ctx, slot, 1e-8, 1e-12, 1e4, 1 << 30, 0));
   double* hs = ctx->h_scalars + (size_t)slot * S_SLOT_SIZE;
@@ -575,32 +568,24 @@ int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply
   const Coef coef = dpp_coef(ctx);
   double* dtab = ctx->d_dtab;
   DPP_CHECK(cg_fused_table(ctx, coef, 2, DPP_PC_JACOBI, dtab));
-  const double* rr[2] = {K->r, K->r + n};
-  double* xx[2] = {K->x, K->x + n};
-  double* ww[2] = {K->w, K->w + n};
-  double* P[2] = {K->p, K->z};
   const int fld[2] = {0, 1};
   cudaEvent_t e0, e1;
   DPP_CUDA(cudaEventCreate(&e0));
   DPP_CUDA(cudaEventCreate(&e1));
   float ms = 0;
   int nb = 0;
-  for (int pass = 0; pass < 2; ++pass) {
+  double* outs[3] = {apply_ms, update_ms, matvec_ms};
+  for (int pass = 0; pass < 3; ++pass) {
     for (int i = -warmup; i < reps; ++i) {
       if (i == 0) DPP_CUDA(cudaEventRecord(e0, ctx->stream));
-      if (pass == 0) {
-        const double* pin[2] = {P[i & 1], P[i & 1] + n};
-        double* pout[2] = {P[(i + 1) & 1], P[(i + 1) & 1] + n};
-        DPP_CHECK(cg_fused_apply(ctx, 2, coef, rr, pin, pout, xx, ww, slot, dtab, &nb));
-        DPP_CHECK(structured_fix_rows(ctx, 2, fld, ww, pout, 1, S + S_REASON));
-      } else {
-        DPP_CHECK(cg_fused_r_update(ctx, L, K->r, K->w, slot, dtab, &nb));
-      }
+      if (pass == 0) DPP_CHECK(cg_fused_apply(ctx, 2, coef, i + warmup, fld, slot, dtab, &nb));
+      else if (pass == 1) DPP_CHECK(cg_fused_r_update(ctx, 2, slot, dtab, &nb));
+      else DPP_CHECK(cg_fused_plain_apply(ctx, 2, coef, true, &nb));
     }
     DPP_CUDA(cudaEventRecord(e1, ctx->stream));
     DPP_CUDA(cudaEventSynchronize(e1));
     DPP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    *(pass == 0 ? apply_ms : update_ms) = (double)ms / reps;
+    *outs[pass] = (double)ms / reps;
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);

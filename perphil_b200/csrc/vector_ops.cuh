@@ -46,16 +46,18 @@ int cg_p_update(dpp_context* ctx, const VecLayout& L, double* p, const double* r
 int cg_xr_update(dpp_context* ctx, const VecLayout& L, double* x, double* r, const double* p, const double* w,
                  const double* dinv, bool fused_pc, int slot, PostOp post);
 
-// fused CG iteration on uniform grids (cg_fused_uniform.cu)
+// fused CG iteration on uniform grids (cg_fused_uniform.cu): padded private layout + TMA loads
 bool cg_fused_available(const dpp_context* ctx, int nf, int operator_mode, int pc_type);
 int cg_fused_table(dpp_context* ctx, const Coef& c, int nf, int pc_type, double* d_tab);
-int cg_fused_rz_init(dpp_context* ctx, const VecLayout& L, const double* r, int slot, const double* dtab, int* nblocks);
-int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, const double* const* r, const double* const* pin,
-                   double* const* pout, double* const* x, double* const* w, int slot, const double* dtab,
+int cg_fused_begin(dpp_context* ctx, int nf, const double* b);
+int cg_fused_rz_init(dpp_context* ctx, int nf, int slot, const double* dtab, int* nblocks);
+int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const int* fld, int slot, const double* dtab,
                    int* n_partial_blocks);
-int cg_fused_r_update(dpp_context* ctx, const VecLayout& L, double* r, const double* w, int slot, const double* dtab,
-                      int* nblocks);
-int cg_fused_x_finalize(dpp_context* ctx, const VecLayout& L, double* x, const double* p, int slot);
+int cg_fused_r_update(dpp_context* ctx, int nf, int slot, const double* dtab, int* nblocks);
+int cg_fused_x_finalize(dpp_context* ctx, int nf, long long its, int slot, double* x);
+int cg_fused_halo_r(dpp_context* ctx, int nf);
+int cg_fused_plain_apply(dpp_context* ctx, int nf, const Coef& c, bool want_dot, int* n_partial_blocks);
+int cg_fused_pad_from(dpp_context* ctx, int which /*0 r, 1 p0, 2 p1, 3 w, 4 x*/, const double* src);
 
 // GMRES kernels
 int gmres_mdot(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, const double* w, int slot);

@@ -443,8 +443,8 @@ def test_fused_cg_partial_and_no_dirichlet():
 def test_fused_cg_kernel_timer_runs():
     W, p, bcs, _ = make_problem((16, 16, 16), 1)
     h = configured_handle(W, p, bcs)
-    a, u = h.time_cg_kernels(reps=3, warmup=1)
-    assert a > 0 and u > 0
+    a, u, m = h.time_cg_kernels(reps=3, warmup=1)
+    assert a > 0 and u > 0 and m > 0
     # the timer scribbles on the work vectors only: a solve afterwards is unaffected
     sol = pb.solve_dpp(W, p, bcs, solver_parameters=pb.B200_CG_JACOBI_PARAMS)
     assert sol.iteration_number == 31
