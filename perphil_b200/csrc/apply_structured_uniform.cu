@@ -84,8 +84,16 @@ __global__ void __launch_bounds__(NT, 2) k_apply_uniform(const UArgs s) {
   // contiguous ranges (one CTA each, a single wave of 2 CTAs per SM); a range is processed as runs of
   // consecutive planes of one tile (2 redundant planes per run).
   const long long total = (long long)s.ntj * s.ntk * nown;
-  long long wbeg = (total * blockIdx.x) / gridDim.x;
-  const long long wend = (total * (blockIdx.x + 1)) / gridDim.x;
+  long long wbeg, wend;
+  if (s.nseg > 0) {  // one (tile, x-segment) item per CTA, tile index fastest
+    const int ntiles = s.ntj * s.ntk;
+    const int tile_ = blockIdx.x % ntiles, seg_ = blockIdx.x / ntiles;
+    wbeg = (long long)tile_ * nown + ((long long)seg_ * nown) / s.nseg;
+    wend = (long long)tile_ * nown + ((long long)(seg_ + 1) * nown) / s.nseg;
+  } else {           // persistent: equal contiguous shares of the (tile, plane) steps
+    wbeg = (total * blockIdx.x) / gridDim.x;
+    wend = (total * (blockIdx.x + 1)) / gridDim.x;
+  }
   for (; wbeg < wend;) {
   const int tile = (int)(wbeg / nown);
   const int run_a = (int)(wbeg - (long long)tile * nown);
@@ -372,8 +380,14 @@ int structured_apply_uniform(dpp_context* ctx, const OpArgs& a, int* n_partial_b
   // one wave of persistent CTAs (2 per SM) with equal shares of the (tile, plane) steps; small grids
   // get fewer CTAs so that a run stays >= ~8 planes
   const long long total = (long long)tiles * nown;
-  const int nctas = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count * 2, total / 8));
-  s.nseg = 1;
+  int nctas;
+  if (tiles <= kMaxPartialBlocks / 2) {
+    s.nseg = choose_x_segments(tiles, nown, ctx->sm_count * 2, kMaxPartialBlocks);
+    nctas = tiles * s.nseg;
+  } else {
+    s.nseg = 0;
+    nctas = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count * 2, total / 8));
+  }
   dim3 grid(nctas), block(TK, TY);
   if (a.nf == 2)
     k_apply_uniform<2><<<grid, block, 0, ctx->stream>>>(s);

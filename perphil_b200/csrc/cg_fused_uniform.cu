@@ -58,7 +58,7 @@ struct FArgs {
   Coef c;
   double* dot_partials;
   int i_begin, i_end;
-  int ntj, ntk;
+  int ntj, ntk, nseg;
   const double* S;           // scalar slot of the solver (null in plain-apply mode)
   const double* dtab;        // [2][8] reciprocal diagonal per boundary class bx*4 + by*2 + bz
   int dom_lo, dom_hi;        // local plane 0 / n[0]-1 lies on the domain boundary (else it is a ghost plane)
@@ -143,8 +143,16 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
   // contiguous ranges (one CTA each, one wave of 2 CTAs per SM); a range is processed as runs of
   // consecutive planes of one tile (2 redundant planes per run).
   const long long total = (long long)s.ntj * s.ntk * nown;
-  long long wbeg = (total * blockIdx.x) / gridDim.x;
-  const long long wend = (total * (blockIdx.x + 1)) / gridDim.x;
+  long long wbeg, wend;
+  if (s.nseg > 0) {  // one (tile, x-segment) item per CTA, tile index fastest
+    const int ntiles = s.ntj * s.ntk;
+    const int tile_ = blockIdx.x % ntiles, seg_ = blockIdx.x / ntiles;
+    wbeg = (long long)tile_ * nown + ((long long)seg_ * nown) / s.nseg;
+    wend = (long long)tile_ * nown + ((long long)(seg_ + 1) * nown) / s.nseg;
+  } else {           // persistent: equal contiguous shares of the (tile, plane) steps
+    wbeg = (total * blockIdx.x) / gridDim.x;
+    wend = (total * (blockIdx.x + 1)) / gridDim.x;
+  }
   for (; wbeg < wend;) {
     const int tile = (int)(wbeg / nown);
     const int run_a = (int)(wbeg - (long long)tile * nown);
@@ -626,7 +634,7 @@ static int make_map(dpp_context* ctx, FusedState* F, CUtensorMap* m, double* bas
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult rc = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     ctx->set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
     return DPP_ERR_CUDA;
@@ -692,10 +700,16 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
   const int tiles = s.ntk * s.ntj;
   const int nown = s.i_end - s.i_begin;
   if (nown <= 0) { *n_partial_blocks = 0; return DPP_OK; }
-  // one wave of persistent CTAs (2 per SM), each with an equal share of the (tile, plane) steps; small
-  // grids get fewer CTAs so that a run stays >= ~8 planes (2 redundant planes per run)
+  // (tile, x-segment) items in hardware dispatch order; see choose_x_segments()
   const long long total = (long long)tiles * nown;
-  const int nctas = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count * 2, total / 8));
+  int nctas;
+  if (tiles <= kMaxPartialBlocks / 2) {
+    s.nseg = choose_x_segments(tiles, nown, ctx->sm_count * 2, kMaxPartialBlocks);
+    nctas = tiles * s.nseg;
+  } else {  // very wide planes: persistent partition (partials scratch is bounded)
+    s.nseg = 0;
+    nctas = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count * 2, total / 8));
+  }
   if (!F->attr_set) {
     DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<2>)));
     DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));

@@ -148,6 +148,25 @@ constexpr int kMaxPartialBlocks = 4096;
 constexpr int kMaxDotWidth = 40;   // >= gmres restart + 2
 constexpr int kNumScalars = 256;
 
+// Number of x-segments for the plane-streaming kernels: CTAs are (tile, segment) items dispatched by the
+// hardware in linear order (tile fastest), so all tiles of a segment run concurrently (halo rows/columns
+// of neighbouring tiles then hit in L2 -- a fully persistent partition loses that, measured: 2x DRAM
+// reads).  Cost model: rounds of `capacity` resident CTAs x (planes per segment + 2 redundant planes +
+// prologue); returns the segment count with the smallest cost.
+inline int choose_x_segments(int tiles, int nown, int capacity, int max_ctas) {
+  int best = 1;
+  long long best_cost = -1;
+  for (int nseg = 1; nseg <= nown; ++nseg) {
+    if ((long long)tiles * nseg > max_ctas && nseg > 1) break;
+    const int len = (nown + nseg - 1) / nseg;
+    if (len < 4 && nseg > 1) break;
+    const long long rounds = ((long long)tiles * nseg + capacity - 1) / capacity;
+    const long long cost = rounds * (len + 2 + 2);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nseg; }
+  }
+  return best;
+}
+
 // ---- apply_structured.cu
 int structured_detect_and_setup(dpp_context* ctx, const int32_t* cnm_host, const double* coords_host,
                                 const int32_t* ccnm_host);
