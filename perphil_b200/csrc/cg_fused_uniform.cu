@@ -596,6 +596,7 @@ struct FusedState {
   CUtensorMap tm[2][4];   // [nf-1][r, p0, p1, x]
   int32_t* bc_pad[2] = {nullptr, nullptr};
   long long bc_count[2] = {0, 0};
+  long long bc_cap[2] = {0, 0};
   int64_t bc_gen[2] = {-1, -1};   // ctx->bc_gen the padded ids were derived from
   bool attr_set = false;
 };
@@ -822,12 +823,18 @@ int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const 
   for (int f = 0; f < nf; ++f) {
     const int fl = fld[f];
     if (F->bc_gen[fl] != ctx->bc_gen[fl]) {
-      if (F->bc_pad[fl]) cudaFree(F->bc_pad[fl]);
-      F->bc_pad[fl] = nullptr;
+      if (ctx->n_bc[fl] > F->bc_cap[fl]) {
+        if (F->bc_pad[fl]) cudaFree(F->bc_pad[fl]);
+        F->bc_pad[fl] = nullptr;
+        F->bc_cap[fl] = 0;
+      }
       F->bc_count[fl] = ctx->n_bc[fl];
       F->bc_gen[fl] = ctx->bc_gen[fl];
       if (ctx->n_bc[fl] > 0) {
-        DPP_CHECK(dev_alloc(ctx, &F->bc_pad[fl], ctx->n_bc[fl]));
+        if (!F->bc_pad[fl]) {
+          DPP_CHECK(dev_alloc(ctx, &F->bc_pad[fl], ctx->n_bc[fl]));
+          F->bc_cap[fl] = ctx->n_bc[fl];
+        }
         const int blocks = (int)std::min<long long>((ctx->n_bc[fl] + 255) / 256, 4096);
         k_pad_ids<<<blocks, 256, 0, ctx->stream>>>(ctx->n_bc[fl], ctx->d_bc_nodes[fl], g, F->bc_pad[fl]);
         ctx->launches++;

@@ -123,7 +123,7 @@ void dpp_destroy(dpp_handle ctx) {
   dpp::comm_destroy(ctx);
   void* ptrs[] = {ctx->d_cnm, ctx->d_coords, ctx->ccnm_alias ? nullptr : ctx->d_ccnm, ctx->d_tables, ctx->d_adj_ptr,
                   ctx->d_adj_cell, ctx->d_adj_loc, ctx->d_cell_geom, ctx->d_mask, ctx->d_g, ctx->d_solution, ctx->d_diag,
-                  ctx->d_partials, ctx->d_scalars, ctx->d_dtab, ctx->d_hist[0], ctx->d_hist[1], ctx->d_premask, ctx->d_bc_nodes[0], ctx->d_bc_nodes[1]};
+                  ctx->d_partials, ctx->d_scalars, ctx->d_dtab, ctx->d_hist[0], ctx->d_hist[1], ctx->d_premask, ctx->d_bc_nodes[0], ctx->d_bc_nodes[1], ctx->d_bc_vals};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -204,23 +204,29 @@ int dpp_set_dirichlet(dpp_handle ctx, int field, int64_t n, const int32_t* nodes
   DPP_CUDA(cudaMemsetAsync(ctx->d_mask + field * nn, 0, nn, ctx->stream));
   DPP_CUDA(cudaMemsetAsync(ctx->d_g + field * nn, 0, sizeof(double) * nn, ctx->stream));
   if (n > 0) {
-    int32_t* d_nodes = nullptr;
-    double* d_vals = nullptr;
-    DPP_CUDA(cudaMalloc((void**)&d_nodes, sizeof(int32_t) * n));
-    DPP_CUDA(cudaMalloc((void**)&d_vals, sizeof(double) * n));
+    // device buffers are kept and only grow: no cudaMalloc/cudaFree on the per-solve path
+    if (n > ctx->bc_cap[field]) {
+      if (ctx->d_bc_nodes[field]) cudaFree(ctx->d_bc_nodes[field]);
+      ctx->d_bc_nodes[field] = nullptr;
+      ctx->bc_cap[field] = 0;
+      DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_bc_nodes[field], n));
+      ctx->bc_cap[field] = n;
+    }
+    if (n > ctx->bc_vals_cap) {
+      if (ctx->d_bc_vals) cudaFree(ctx->d_bc_vals);
+      ctx->d_bc_vals = nullptr;
+      ctx->bc_vals_cap = 0;
+      DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_bc_vals, n));
+      ctx->bc_vals_cap = n;
+    }
+    int32_t* d_nodes = ctx->d_bc_nodes[field];  // kept: row-elimination fix-up of the uniform-grid apply
     DPP_CUDA(cudaMemcpyAsync(d_nodes, nodes, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-    DPP_CUDA(cudaMemcpyAsync(d_vals, values, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    DPP_CUDA(cudaMemcpyAsync(ctx->d_bc_vals, values, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4096);
-    k_scatter_bc<<<blocks, 256, 0, ctx->stream>>>(n, d_nodes, d_vals, ctx->d_mask + field * nn, ctx->d_g + field * nn);
+    k_scatter_bc<<<blocks, 256, 0, ctx->stream>>>(n, d_nodes, ctx->d_bc_vals, ctx->d_mask + field * nn, ctx->d_g + field * nn);
     ctx->launches++;
     DPP_CUDA(cudaGetLastError());
-    DPP_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_vals);
-    if (ctx->d_bc_nodes[field]) cudaFree(ctx->d_bc_nodes[field]);
-    ctx->d_bc_nodes[field] = d_nodes;  // kept: row-elimination fix-up of the uniform-grid apply
-  } else if (ctx->d_bc_nodes[field]) {
-    cudaFree(ctx->d_bc_nodes[field]);
-    ctx->d_bc_nodes[field] = nullptr;
+    DPP_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller may reuse its host buffers
   }
   ctx->n_bc[field] = n;
   ctx->bc_gen[field]++;

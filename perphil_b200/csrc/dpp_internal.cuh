@@ -113,6 +113,9 @@ struct dpp_context {
   bool have_bc[2] = {false, false};
   int32_t* d_bc_nodes[2] = {nullptr, nullptr};  // constrained node ids per field
   int64_t n_bc[2] = {0, 0};
+  int64_t bc_cap[2] = {0, 0};     // capacity of d_bc_nodes
+  double* d_bc_vals = nullptr;    // upload staging for Dirichlet values
+  int64_t bc_vals_cap = 0;
   int64_t bc_gen[2] = {0, 0};     // bumped by every dpp_set_dirichlet of that field
 
   // partition
