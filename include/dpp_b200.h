@@ -53,7 +53,8 @@ typedef enum { DPP_KERNEL_GENERAL = 0, DPP_KERNEL_STRUCTURED = 1 } dpp_kernel_fa
 enum {
   DPP_CONVERGED_RTOL = 2, DPP_CONVERGED_ATOL = 3, DPP_CONVERGED_ITS = 4,
   DPP_DIVERGED_ITS = -3, DPP_DIVERGED_DTOL = -4, DPP_DIVERGED_BREAKDOWN = -5,
-  DPP_DIVERGED_INDEFINITE_MAT = -10, DPP_DIVERGED_NANORINF = -9
+  DPP_DIVERGED_INDEFINITE_MAT = -10, DPP_DIVERGED_NANORINF = -9,
+  DPP_DIVERGED_COMM_TIMEOUT = -100  /* a peer never arrived at a reduction (not a PETSc reason) */
 };
 
 typedef struct {
@@ -94,6 +95,7 @@ typedef struct {
   int64_t n_nodes, n_cells, n_owned_nodes;
   int32_t rank, world;
   int32_t sm_count;
+  int32_t peer_memory;       /* 1: CUDA IPC halo push + mailbox allreduce active (dpp_comm_ipc_import) */
   int64_t device_bytes;      /* device memory held by the handle */
 } dpp_info;
 
@@ -136,6 +138,16 @@ int dpp_nccl_unique_id(void* out128);
 /* one neighbour: local node ids whose values are sent to / received from `peer` before an apply */
 int dpp_comm_add_neighbor(dpp_handle h, int peer, int64_t n_send, const int32_t* send_nodes_host,
                           int64_t n_recv, const int32_t* recv_nodes_host);
+
+/* Peer-memory fast path of the fused Jacobi-CG iteration (optional; one box, NVLink/NVSwitch): every
+ * rank exports CUDA IPC handles of its residual vector and of a small mailbox; after the import the
+ * r-update kernel stores its boundary planes straight into the neighbours' ghost planes and the Krylov
+ * scalars are summed through the mailboxes inside the reduction kernel (no NCCL call per iteration).
+ * Protocol: dpp_comm_init + dpp_comm_add_neighbor on every rank, then dpp_comm_ipc_export on every rank,
+ * all-gather the blobs (host layer), dpp_comm_ipc_import on every rank.  Without it the NCCL path runs. */
+int dpp_comm_ipc_blob_size(void);
+int dpp_comm_ipc_export(dpp_handle h, void* blob_out);
+int dpp_comm_ipc_import(dpp_handle h, const void* blobs_all_ranks);
 
 /* ---- operator ------------------------------------------------------------------------------- */
 

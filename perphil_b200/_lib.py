@@ -46,7 +46,7 @@ class DppInfo(C.Structure):
         ("kernel_family", C.c_int32), ("dim", C.c_int32), ("degree", C.c_int32),
         ("grid_nodes", C.c_int32 * 3),
         ("n_nodes", C.c_int64), ("n_cells", C.c_int64), ("n_owned_nodes", C.c_int64),
-        ("rank", C.c_int32), ("world", C.c_int32), ("sm_count", C.c_int32),
+        ("rank", C.c_int32), ("world", C.c_int32), ("sm_count", C.c_int32), ("peer_memory", C.c_int32),
         ("device_bytes", C.c_int64),
     ]
 
@@ -63,6 +63,9 @@ _PROTOTYPES = {
     "dpp_set_dirichlet": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "dpp_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64]),
     "dpp_comm_add_neighbor": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dpp_comm_ipc_blob_size": (C.c_int, []),
+    "dpp_comm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dpp_comm_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dpp_apply_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dpp_apply_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dpp_get_diagonal_host": (C.c_int, [C.c_void_p, C.c_void_p]),

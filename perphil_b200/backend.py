@@ -98,6 +98,19 @@ class DppHandle:
         self._check(self._lib.dpp_comm_add_neighbor(self._h, peer, s.size, _ptr(s), r.size, _ptr(r)),
                     "dpp_comm_add_neighbor")
 
+    def comm_ipc_export(self) -> bytes:
+        """This rank's CUDA IPC blob (residual vector + mailbox handles) for the peer-memory fast path."""
+        n = self._lib.dpp_comm_ipc_blob_size()
+        buf = C.create_string_buffer(n)
+        self._check(self._lib.dpp_comm_ipc_export(self._h, buf), "dpp_comm_ipc_export")
+        return buf.raw
+
+    def comm_ipc_import(self, blobs) -> None:
+        """blobs: the exported blobs of ALL ranks, in rank order."""
+        raw = b"".join(blobs)
+        buf = C.create_string_buffer(raw, len(raw))
+        self._check(self._lib.dpp_comm_ipc_import(self._h, buf), "dpp_comm_ipc_import")
+
     # -- operator
     def apply(self, x: np.ndarray, assembled: bool = False) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)

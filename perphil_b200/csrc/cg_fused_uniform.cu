@@ -366,6 +366,10 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
 // ---------------------------------------------------------------------------------------------
 // r -= alpha w ; z = dinv .* r (registers only) ; partial <r,z>, <z,z>.   Padded layout, dinv from
 // the class table.  Pad columns hold zeros in r and w and therefore stay zero.
+// Slab-partitioned runs with peer memory: the first / last owned plane of the new r is ALSO stored into
+// the ghost plane of the lower / upper neighbour (fused halo push over NVLink; the mailbox reduction
+// that follows publishes its flag after a system fence, which is what tells the neighbour the plane
+// has landed).
 // ---------------------------------------------------------------------------------------------
 struct RArgs {
   int nf;
@@ -380,6 +384,8 @@ struct RArgs {
   unsigned long long mag_k, mag_j;   // magic multipliers: q / pitch = (q * mag_k) >> sh_k   for q < 2^31
   unsigned sh_k, sh_j;
   int dom_lo, dom_hi;
+  long long plane;           // padded plane (doubles)
+  IpcHalo halo;              // peer residual vectors: boundary planes are stored there as well
 };
 
 constexpr int VT = 256;
@@ -403,6 +409,13 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
     for (int w = 0; w < VT / 32; ++w) t += sm[w];
   }
   return t;
+}
+
+__device__ __forceinline__ void push_halo(const RArgs& a, int f, long long q, double v) {
+  if (a.halo.peer_r[0] != nullptr && q < a.ob + a.plane)
+    a.halo.peer_r[0][f * a.halo.peer_field[0] + a.halo.peer_ghost_off[0] + (q - a.ob)] = v;
+  if (a.halo.peer_r[1] != nullptr && q >= a.oe - a.plane)
+    a.halo.peer_r[1][f * a.halo.peer_field[1] + a.halo.peer_ghost_off[1] + (q - (a.oe - a.plane))] = v;
 }
 
 __device__ __forceinline__ int node_class(const RArgs& a, unsigned q) {
@@ -448,6 +461,7 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
       if (!INIT) {
         rn = fma(-alpha, wv[u], rv[u]);
         rf[q + u * VT] = rn;
+        push_halo(a, f, q + u * VT, rn);
       }
       const double zv = tf[node_class(a, (unsigned)(q + u * VT))] * rn;
       srz = fma(rn, zv, srz);
@@ -459,6 +473,7 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
     if (!INIT) {
       rn = fma(-alpha, wf[q], rn);
       rf[q] = rn;
+      push_halo(a, f, q, rn);
     }
     const double zv = tf[node_class(a, (unsigned)q)] * rn;
     srz = fma(rn, zv, srz);
@@ -470,6 +485,16 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
     const size_t bb = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
     a.partials[bb * 2] = t0;
     a.partials[bb * 2 + 1] = t1;
+  }
+}
+
+// boundary planes of r -> the neighbours' ghost planes (start of a solve)
+__global__ void __launch_bounds__(VT) k_push_planes(const RArgs a) {
+  const int f = blockIdx.y;
+  const double* rf = a.r + (long long)f * a.field;
+  for (long long t = (long long)blockIdx.x * VT + threadIdx.x; t < a.plane; t += (long long)gridDim.x * VT) {
+    push_halo(a, f, a.ob + t, rf[a.ob + t]);
+    if (a.oe - a.plane != a.ob) push_halo(a, f, a.oe - a.plane + t, rf[a.oe - a.plane + t]);
   }
 }
 
@@ -751,6 +776,8 @@ static int make_rargs(dpp_context* ctx, FusedState* F, int nf, int slot, const d
   magic_div(a.nj, &a.mag_j, &a.sh_j);
   a.dom_lo = ctx->dom_lo;
   a.dom_hi = ctx->dom_hi;
+  a.plane = F->plane;
+  a.halo = comm_ipc_halo(ctx);
   *out = a;
   return DPP_OK;
 }
@@ -876,11 +903,35 @@ int cg_fused_x_finalize(dpp_context* ctx, int nf, long long its, int slot, doubl
   return DPP_OK;
 }
 
-// ghost planes of r (padded layout) for slab-partitioned runs
-int cg_fused_halo_r(dpp_context* ctx, int nf) {
+double* cg_fused_r_buffer(dpp_context* ctx, long long* field, long long* plane) {
+  if (!(ctx->family == DPP_KERNEL_STRUCTURED && ctx->grid.band == 1 && ctx->grid_uniform && encode_fn() != nullptr))
+    return nullptr;
+  FusedState* F = nullptr;
+  if (fused_state(ctx, &F) != DPP_OK) return nullptr;
+  *field = F->field;
+  *plane = F->plane;
+  return F->buf[0];
+}
+
+// ghost planes of r (padded layout) for slab-partitioned runs.  `after_update`: the r-update kernel has
+// already pushed them (peer-memory path); otherwise (start of a solve) exchange explicitly.
+int cg_fused_halo_r(dpp_context* ctx, int nf, bool after_update, int slot) {
   if (ctx->world <= 1) return DPP_OK;
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
+  if (comm_ipc_ready(ctx)) {
+    if (after_update) return DPP_OK;
+    // every rank must have finished writing its own r (ghost rows included) before neighbours store into
+    // it: a zero-width mailbox reduction is the barrier; the push is then fenced by the next reduction
+    DPP_CHECK(reduce_partials(ctx, 0, 1, slot, POST_NONE, 30));
+    RArgs a{};
+    DPP_CHECK(make_rargs(ctx, F, nf, slot, ctx->d_dtab, &a));
+    dim3 grid((unsigned)std::min<long long>((F->plane + VT - 1) / VT, (long long)ctx->sm_count * 4), nf);
+    k_push_planes<<<grid, VT, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    DPP_CUDA(cudaGetLastError());
+    return DPP_OK;
+  }
   const long long uplane = (long long)ctx->grid.n[1] * ctx->grid.n[2];
   return comm_halo_planes(ctx, F->buf[0], nf, F->field, F->plane, (int)(ctx->owned_begin / uplane),
                           (int)(ctx->owned_end / uplane));

@@ -69,9 +69,25 @@ struct Neighbor {
   int64_t send0 = 0, recv0 = 0;
 };
 
+struct IpcBlob {  // what every rank publishes (POD; all-gathered by the host layer)
+  cudaIpcMemHandle_t r_handle;
+  cudaIpcMemHandle_t mbox_handle;
+  int64_t field, plane;      // padded strides of the residual vector (doubles)
+  int32_t i_begin, i_end;    // owned local planes
+  int32_t rank, valid;
+};
+
 struct Comm {
   ncclComm_t comm = nullptr;
   std::vector<Neighbor> nbrs;
+  // peer-memory fast path
+  bool ipc = false;
+  double* mbox = nullptr;                 // own mailbox [2][world][kMboxEntry]
+  double* mbox_peer[kMaxIpcRanks] = {};   // mapped mailboxes of the other ranks
+  double* r_peer[2] = {nullptr, nullptr}; // mapped residual vectors of rank-1 / rank+1
+  long long r_peer_field[2] = {0, 0}, r_peer_ghost_off[2] = {0, 0};
+  std::vector<void*> mapped;              // everything opened with cudaIpcOpenMemHandle
+  unsigned long long seq = 0;
 };
 
 namespace {
@@ -174,9 +190,36 @@ int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n) {
   return DPP_OK;
 }
 
+bool comm_ipc_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc; }
+
+IpcReduce comm_ipc_next_reduce(dpp_context* ctx) {
+  Comm* C = ctx->comm;
+  IpcReduce a{};
+  a.local = C->mbox;
+  for (int r = 0; r < ctx->world; ++r) a.peer[r] = (r == ctx->rank) ? C->mbox : C->mbox_peer[r];
+  a.rank = ctx->rank;
+  a.world = ctx->world;
+  a.seq = ++C->seq;
+  return a;
+}
+
+IpcHalo comm_ipc_halo(const dpp_context* ctx) {
+  IpcHalo h{};
+  const Comm* C = ctx->comm;
+  if (C && C->ipc)
+    for (int s = 0; s < 2; ++s) {
+      h.peer_r[s] = C->r_peer[s];
+      h.peer_field[s] = C->r_peer_field[s];
+      h.peer_ghost_off[s] = C->r_peer_ghost_off[s];
+    }
+  return h;
+}
+
 void comm_destroy(dpp_context* ctx) {
   Comm* C = ctx->comm;
   if (!C) return;
+  for (void* m : C->mapped) cudaIpcCloseMemHandle(m);
+  if (C->mbox) cudaFree(C->mbox);
   for (Neighbor& nb : C->nbrs) {
     void* p[] = {nb.d_send_idx, nb.d_recv_idx, nb.d_sendbuf, nb.d_recvbuf};
     for (void* q : p)
@@ -228,6 +271,77 @@ int dpp_comm_init(dpp_handle ctx, int rank, int world, const void* unique_id, in
   ncclUniqueId id;
   memcpy(&id, unique_id, 128);
   DPP_NCCL(nccl().CommInitRank(&ctx->comm->comm, world, id, rank));
+  return DPP_OK;
+}
+
+int dpp_comm_ipc_blob_size(void) { return (int)sizeof(dpp::IpcBlob); }
+
+int dpp_comm_ipc_export(dpp_handle ctx, void* blob_out) {
+  if (!ctx || !blob_out) return DPP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  dpp::IpcBlob b;
+  memset(&b, 0, sizeof(b));
+  b.rank = ctx->rank;
+  dpp::Comm* C = ctx->comm;
+  long long field = 0, plane = 0;
+  double* r = (C && ctx->world > 1 && ctx->world <= dpp::kMaxIpcRanks && !getenv("DPP_NO_IPC"))
+                  ? dpp::cg_fused_r_buffer(ctx, &field, &plane) : nullptr;
+  if (r != nullptr) {
+    if (!C->mbox) {
+      DPP_CHECK(dpp::dev_alloc(ctx, &C->mbox, 2 * dpp::kMaxIpcRanks * dpp::kMboxEntry));
+      DPP_CUDA(cudaMemset(C->mbox, 0, sizeof(double) * 2 * dpp::kMaxIpcRanks * dpp::kMboxEntry));
+    }
+    const long long uplane = (long long)ctx->grid.n[1] * ctx->grid.n[2];
+    if (cudaIpcGetMemHandle(&b.r_handle, r) == cudaSuccess && cudaIpcGetMemHandle(&b.mbox_handle, C->mbox) == cudaSuccess) {
+      b.field = field;
+      b.plane = plane;
+      b.i_begin = (int32_t)(ctx->owned_begin / uplane);
+      b.i_end = (int32_t)(ctx->owned_end / uplane);
+      b.valid = 1;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  memcpy(blob_out, &b, sizeof(b));
+  return DPP_OK;
+}
+
+int dpp_comm_ipc_import(dpp_handle ctx, const void* blobs) {
+  if (!ctx || !blobs || !ctx->comm) return DPP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  dpp::Comm* C = ctx->comm;
+  C->ipc = false;
+  const dpp::IpcBlob* B = static_cast<const dpp::IpcBlob*>(blobs);
+  if (ctx->world > dpp::kMaxIpcRanks) return DPP_OK;
+  for (int r = 0; r < ctx->world; ++r)
+    if (!B[r].valid || B[r].rank != r) return DPP_OK;  // some rank cannot take part: keep the NCCL path
+  for (int r = 0; r < ctx->world; ++r) {
+    if (r == ctx->rank) continue;
+    void* m = nullptr;
+    if (cudaIpcOpenMemHandle(&m, B[r].mbox_handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      return DPP_OK;  // no peer access between these GPUs: NCCL path
+    }
+    C->mapped.push_back(m);
+    C->mbox_peer[r] = static_cast<double*>(m);
+  }
+  for (int s = 0; s < 2; ++s) {
+    const int peer = s == 0 ? ctx->rank - 1 : ctx->rank + 1;
+    if (peer < 0 || peer >= ctx->world) continue;
+    void* m = nullptr;
+    if (cudaIpcOpenMemHandle(&m, B[peer].r_handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      return DPP_OK;
+    }
+    C->mapped.push_back(m);
+    C->r_peer[s] = static_cast<double*>(m);
+    C->r_peer_field[s] = B[peer].field;
+    // my first owned plane is the lower neighbour's upper ghost (its local plane i_end);
+    // my last owned plane is the upper neighbour's lower ghost (its local plane i_begin - 1)
+    C->r_peer_ghost_off[s] = (s == 0 ? (long long)B[peer].i_end : (long long)B[peer].i_begin - 1) * B[peer].plane;
+    if (C->r_peer_ghost_off[s] < 0) return DPP_OK;
+  }
+  C->ipc = true;
   return DPP_OK;
 }
 

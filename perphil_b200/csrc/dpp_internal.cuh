@@ -203,6 +203,26 @@ int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n);
 int comm_halo_planes(dpp_context* ctx, double* base, int nf, long long field_stride, long long plane_elems, int i_begin,
                      int i_end);
 void cg_fused_destroy(dpp_context* ctx);
+
+// peer-memory (CUDA IPC) fast path, comm.cu
+constexpr int kMaxIpcRanks = 16;
+constexpr int kMboxEntry = 8;      // doubles per mailbox entry: 7 values + sequence flag
+struct IpcReduce {                 // kernel argument of the mailbox allreduce
+  double* local;                   // [2 slots][world][kMboxEntry]
+  double* peer[kMaxIpcRanks];      // the same array of every rank (peer[rank] == local)
+  int rank, world;
+  unsigned long long seq;
+};
+struct IpcHalo {                   // kernel argument of the halo push (padded layout)
+  double* peer_r[2];               // lower / upper neighbour's residual vector (null: none)
+  long long peer_field[2];         // their padded field stride
+  long long peer_ghost_off[2];     // offset of the ghost plane that mirrors my boundary plane
+};
+bool comm_ipc_ready(const dpp_context* ctx);
+IpcReduce comm_ipc_next_reduce(dpp_context* ctx);   // bumps the sequence number
+IpcHalo comm_ipc_halo(const dpp_context* ctx);
+// residual buffer registration (cg_fused_uniform.cu owns the memory)
+double* cg_fused_r_buffer(dpp_context* ctx, long long* field, long long* plane);
 void comm_destroy(dpp_context* ctx);
 
 // ---- assemble_csr.cu

@@ -164,7 +164,7 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
     double* dtab = ctx->d_dtab + (size_t)slot * 16;
     DPP_CHECK(cg_fused_table(ctx, coef, op.nf, pc.type, dtab));
     DPP_CHECK(cg_fused_begin(ctx, op.nf, b));
-    DPP_CHECK(cg_fused_halo_r(ctx, op.nf));
+    DPP_CHECK(cg_fused_halo_r(ctx, op.nf, false, slot));
     int nb = 0;
     DPP_CHECK(cg_fused_rz_init(ctx, op.nf, slot, dtab, &nb));
     DPP_CHECK(reduce_partials(ctx, nb, 2, slot, POST_CG_INIT));
@@ -179,7 +179,7 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
         DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
         DPP_CHECK(cg_fused_r_update(ctx, op.nf, slot, dtab, &nb));
         DPP_CHECK(reduce_partials(ctx, nb, 2, slot, POST_CG_RZ));
-        DPP_CHECK(cg_fused_halo_r(ctx, op.nf));
+        DPP_CHECK(cg_fused_halo_r(ctx, op.nf, true, slot));
       }
       DPP_CHECK(scalars_fetch(ctx, slot));
     }
@@ -658,6 +658,10 @@ int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_r
       rc = DPP_ERR_INVALID;
   }
   DPP_CHECK(rc);
+  if (out.reason == DPP_DIVERGED_COMM_TIMEOUT) {
+    ctx->set_error("a peer rank never arrived at a Krylov reduction (peer-memory mailbox timed out)");
+    return DPP_ERR_NCCL;
+  }
   DPP_CUDA(cudaEventRecord(K->ev[2], ctx->stream));
   // u = u0 + d
   if (!ctx->d_solution) DPP_CHECK(dev_alloc(ctx, &ctx->d_solution, 2 * n));

@@ -107,6 +107,58 @@ __global__ void __launch_bounds__(VT) k_reduce_partials(const double* __restrict
 
 __global__ void k_post_only(double* S, double* hist, int post) { apply_post(S, hist, post); }
 
+// Local reduction + all-reduce over the ranks' mailboxes (peer memory, NVLink) + post-op, one block.
+// Every rank writes its partial sums into slot (seq & 1) of EVERY rank's mailbox, flag last; then
+// waits until all ranks' entries of this sequence number have arrived in its own mailbox and adds them
+// in rank order -- the same order everywhere, so all ranks hold bit-identical sums.  Two slots are
+// enough: a rank can run at most one reduction ahead of the slowest one.
+__global__ void __launch_bounds__(VT) k_reduce_partials_ipc(const double* __restrict__ partials, int nblocks, int width,
+                                                             double* S, double* hist, int post, int out_offset,
+                                                             IpcReduce ipc) {
+  __shared__ double sm[VT / 32];
+  __shared__ double vals[kMboxEntry];
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  for (int w = 0; w < width; ++w) {
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += VT) v += partials[(size_t)b * width + w];
+    const double t = block_sum(v, sm);
+    if (threadIdx.x == 0) vals[w] = t;
+  }
+  __syncthreads();
+  const int slot = (int)(ipc.seq & 1ull);
+  const double tag = (double)ipc.seq;
+  if (threadIdx.x < ipc.world) {
+    double* dst = ipc.peer[threadIdx.x] + ((size_t)slot * ipc.world + ipc.rank) * kMboxEntry;
+    for (int w = 0; w < width; ++w) dst[w] = vals[w];
+    __threadfence_system();   // also orders the halo stores of the preceding kernel before the flag
+    *reinterpret_cast<volatile double*>(dst + kMboxEntry - 1) = tag;
+    const volatile double* src = ipc.local + ((size_t)slot * ipc.world + threadIdx.x) * kMboxEntry;
+    const long long t0 = clock64();
+    while (src[kMboxEntry - 1] != tag) {
+      if (clock64() - t0 > 60000000000LL) {  // ~30 s: a peer died; report instead of hanging the GPU
+        timed_out = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (timed_out) {
+      S[S_REASON] = (double)DPP_DIVERGED_COMM_TIMEOUT;
+    } else {
+      for (int w = 0; w < width; ++w) {
+        double t = 0.0;
+        for (int r = 0; r < ipc.world; ++r)
+          t += reinterpret_cast<const volatile double*>(ipc.local)[((size_t)slot * ipc.world + r) * kMboxEntry + w];
+        S[S_TMP + out_offset + w] = t;
+      }
+      apply_post(S, hist, post);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(VT) k_axpby(VecLayout L, double a, const double* x, double b, double* y) {
   const Chunk c = my_chunk(L);
   for (long long i = c.begin + threadIdx.x; i < c.end; i += VT) {
@@ -335,6 +387,13 @@ double* hist_device(dpp_context* ctx, int slot) { return ctx->hist_cap[slot] > 0
 int reduce_partials(dpp_context* ctx, int nblocks, int width, int slot, PostOp post, int out_offset) {
   double* S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
   const bool dist = ctx->world > 1;
+  if (dist && comm_ipc_ready(ctx) && width < kMboxEntry) {
+    k_reduce_partials_ipc<<<1, VT, 0, ctx->stream>>>(ctx->d_partials, nblocks, width, S, hist_device(ctx, slot), (int)post,
+                                                     out_offset, comm_ipc_next_reduce(ctx));
+    ctx->launches++;
+    DPP_CUDA(cudaGetLastError());
+    return DPP_OK;
+  }
   k_reduce_partials<<<1, VT, 0, ctx->stream>>>(ctx->d_partials, nblocks, width, S, hist_device(ctx, slot), (int)post,
                                                dist ? 0 : 1, out_offset);
   ctx->launches++;

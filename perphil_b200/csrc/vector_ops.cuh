@@ -55,7 +55,7 @@ int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const 
                    int* n_partial_blocks);
 int cg_fused_r_update(dpp_context* ctx, int nf, int slot, const double* dtab, int* nblocks);
 int cg_fused_x_finalize(dpp_context* ctx, int nf, long long its, int slot, double* x);
-int cg_fused_halo_r(dpp_context* ctx, int nf);
+int cg_fused_halo_r(dpp_context* ctx, int nf, bool after_update, int slot);
 int cg_fused_plain_apply(dpp_context* ctx, int nf, const Coef& c, bool want_dot, int* n_partial_blocks);
 int cg_fused_pad_from(dpp_context* ctx, int which /*0 r, 1 p0, 2 p1, 3 w, 4 x*/, const double* src);
 

@@ -145,6 +145,13 @@ class SlabComm:
         self._dist.broadcast(t, src=0)
         return bytes(t.cpu().tolist())
 
+    def all_gather_bytes(self, payload: bytes):
+        if self._dist is None:
+            return [payload]
+        out = [None] * self.size
+        self._dist.all_gather_object(out, payload)
+        return out
+
     # -- wire a libdppb200 handle into the slab decomposition
     def attach(self, handle, space_data, V):
         from .backend import nccl_unique_id
@@ -160,6 +167,10 @@ class SlabComm:
         handle.comm_init(self.rank, self.size, uid, ob * plane_nodes, oe * plane_nodes)
         for peer, send, recv in halo_lists(slab, plane_nodes):
             handle.comm_add_neighbor(peer, send, recv)
+        # peer-memory fast path (CUDA IPC over NVLink): exchange the handles of every rank's residual vector
+        # and mailbox; the library falls back to NCCL by itself if any rank cannot take part
+        if self._backend == "nccl":
+            handle.comm_ipc_import(self.all_gather_bytes(handle.comm_ipc_export()))
 
     def destroy(self):
         if self._dist is not None and self._dist.is_initialized():

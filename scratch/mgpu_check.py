@@ -27,7 +27,7 @@ for preset in ("B200_CG_JACOBI_PARAMS", "B200_GMRES_JACOBI_PARAMS", "B200_GMRES_
     for f in range(2):
         a = sol.solution.sub(f).dat.data; b = ref.solution.sub(f).dat.data[lo:hi]
         err = max(err, float(np.linalg.norm(a - b) / np.linalg.norm(b)))
-    print(f"rank {comm.rank}/{comm.size} {preset}: its {sol.iteration_number} vs {ref.iteration_number}, rel err {err:.2e}, solve {info.solve_ms:.2f} ms", flush=True)
+    print(f"rank {comm.rank}/{comm.size} ipc={pb.handle_for(W).info().peer_memory} {preset}: its {sol.iteration_number} vs {ref.iteration_number}, rel err {err:.2e}, solve {info.solve_ms:.2f} ms", flush=True)
     assert abs(sol.iteration_number - ref.iteration_number) <= (0 if "CG_JACOBI" in preset else 2) and err < 1e-7
     pb.release_handles()
 comm.barrier()
