@@ -1,0 +1,166 @@
+// Device-side pieces shared by the reduction kernels (vector_ops.cu) and the fused CG kernels
+// (cg_fused_uniform.cu): deterministic block sums, the PETSc KSPCG bookkeeping that runs on the device
+// after each global reduction, and the reduction epilogue itself (local sum in block order, optional
+// mailbox all-reduce over peer memory, post-op).
+#pragma once
+
+#include "vector_ops.cuh"
+
+namespace dpp {
+namespace {
+
+constexpr int VT = 256;   // threads per block of every kernel that reduces
+constexpr int kFinishSmem = VT / 32 + kMboxEntry + 2;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum in a fixed order; result valid in thread 0 (linear thread id; VT threads per block)
+__device__ __forceinline__ double block_sum(double v, double* sm /*[VT/32]*/) {
+  v = warp_sum(v);
+  const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5;
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 0; w < VT / 32; ++w) t += sm[w];
+  }
+  return t;
+}
+
+__device__ __forceinline__ void apply_post(double* S, double* hist, int post) {
+  // executed by one thread after the reduction values are in S[S_TMP..]
+  if (post == POST_CG_PAP) {
+    if (S[S_REASON] != 0.0) return;  // the apply was a no-op: partials are stale
+    const double pap = S[S_TMP];
+    S[S_PAP] = pap;
+    if (!(pap > 0.0)) {
+      S[S_REASON] = (pap == pap) ? DPP_DIVERGED_INDEFINITE_MAT : DPP_DIVERGED_NANORINF;
+      S[S_XPEND] = 0.0;
+    } else {
+      S[S_ALPHA] = S[S_RZ] / pap;
+      S[S_XPEND] = 1.0;
+    }
+    return;
+  }
+  if (post == POST_CG_INIT || post == POST_CG_RZ) {
+    if (S[S_REASON] != 0.0) return;
+    const double rz = S[S_TMP], zz = S[S_TMP + 1];
+    const double rnorm = sqrt(zz);
+    int its;
+    if (post == POST_CG_INIT) {
+      its = 0;
+      S[S_RZ_OLD] = 1.0;
+      S[S_RNORM0] = rnorm;
+      const double t = S[S_RTOL] * rnorm;
+      S[S_TTOL] = t > S[S_ATOL] ? t : S[S_ATOL];
+    } else {
+      its = (int)S[S_ITS] + 1;
+      S[S_RZ_OLD] = S[S_RZ];
+    }
+    S[S_RZ] = rz;
+    S[S_ZZ] = zz;
+    S[S_RNORM] = rnorm;
+    S[S_ITS] = (double)its;
+    if (hist != nullptr && its < (int)S[S_HISTCAP]) hist[its] = rnorm;
+    // KSPConvergedDefault
+    double reason = 0.0;
+    if (!(rnorm == rnorm) || isinf(rnorm)) reason = DPP_DIVERGED_NANORINF;
+    else if (rnorm <= S[S_TTOL]) reason = (rnorm < S[S_ATOL]) ? DPP_CONVERGED_ATOL : DPP_CONVERGED_RTOL;
+    else if (rnorm >= S[S_DTOL] * S[S_RNORM0]) reason = DPP_DIVERGED_DTOL;
+    else if (rz == 0.0) reason = DPP_CONVERGED_ATOL;
+    else if (its >= (int)S[S_MAXIT]) reason = DPP_DIVERGED_ITS;
+    S[S_REASON] = reason;
+  }
+}
+
+
+// Reduction epilogue run by ONE block of VT threads: S[S_TMP + out_offset + w] = sum over blocks (fixed
+// order) of partials[b*width + w], all-reduced over the ranks' mailboxes when ipc.world > 1, then the
+// post-op.  Mailbox protocol: every rank writes its sums into slot (seq & 1) of EVERY rank's mailbox,
+// flag last (after a system fence, which also orders the halo stores of the producing kernel before the
+// flag); then waits until all ranks' entries of this sequence number arrived in its own mailbox and adds
+// them in rank order -- the same order everywhere, so all ranks hold bit-identical sums.  Two slots are
+// enough: a rank can run at most one reduction ahead of the slowest one.
+// sm: kFinishSmem = VT/32 + kMboxEntry + 2 doubles of shared memory.
+__device__ __forceinline__ void finish_reduction(const double* __restrict__ partials, int nblocks, int width, double* S,
+                                                 double* hist, int post, int out_offset, const IpcReduce& ipc,
+                                                 double* sm) {
+  double* vals = sm + VT / 32;
+  volatile int* timed_out = reinterpret_cast<volatile int*>(sm + VT / 32 + kMboxEntry);
+  const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+  if (tid == 0) *timed_out = 0;
+  for (int w = 0; w < width; ++w) {
+    double v = 0.0;
+    for (int b = tid; b < nblocks; b += VT) v += partials[(size_t)b * width + w];
+    const double t = block_sum(v, sm);
+    if (tid == 0) vals[w] = t;
+  }
+  const bool dist = ipc.world > 1;
+  unsigned long long* seq_sm = reinterpret_cast<unsigned long long*>(sm + VT / 32 + kMboxEntry + 1);
+  if (dist && tid == 0) *seq_sm = ++(*ipc.seq_dev);
+  __syncthreads();
+  const unsigned long long seq = dist ? *seq_sm : 0ull;
+  const int slot = (int)(seq & 1ull);
+  if (dist && tid < ipc.world) {
+    const double tag = (double)seq;
+    double* dst = ipc.peer[tid] + ((size_t)slot * ipc.world + ipc.rank) * kMboxEntry;
+    for (int w = 0; w < width; ++w) dst[w] = vals[w];
+    __threadfence_system();
+    *reinterpret_cast<volatile double*>(dst + kMboxEntry - 1) = tag;
+    const volatile double* src = ipc.local + ((size_t)slot * ipc.world + tid) * kMboxEntry;
+    const long long t0 = clock64();
+    while (src[kMboxEntry - 1] != tag) {
+      if (clock64() - t0 > 60000000000LL) {  // ~30 s: a peer died; report instead of hanging the GPU
+        *timed_out = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (*timed_out) {
+      S[S_REASON] = (double)DPP_DIVERGED_COMM_TIMEOUT;
+    } else {
+      for (int w = 0; w < width; ++w) {
+        double t = vals[w];
+        if (dist) {
+          t = 0.0;
+          for (int r = 0; r < ipc.world; ++r)
+            t += reinterpret_cast<const volatile double*>(ipc.local)[((size_t)slot * ipc.world + r) * kMboxEntry + w];
+        }
+        S[S_TMP + out_offset + w] = t;
+      }
+      apply_post(S, hist, post);
+    }
+  }
+}
+
+// "last block done" hand-over: every block calls this after writing its partial sums; returns true in
+// exactly one block (the last to arrive), whose threads then see all partials.  The counter resets itself.
+__device__ __forceinline__ bool last_block_arrives(unsigned* counter, unsigned nblocks, int* flag_smem) {
+  const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+  __syncthreads();                       // this block's partial has been written by its thread 0
+  if (tid == 0) {
+    __threadfence();
+    const unsigned ticket = atomicAdd(counter, 1u);
+    const int last = ticket == nblocks - 1;
+    if (last) {
+      *counter = 0;
+      __threadfence();
+    }
+    *flag_smem = last;
+  }
+  __syncthreads();
+  return *flag_smem != 0;
+}
+
+}  // namespace
+}  // namespace dpp

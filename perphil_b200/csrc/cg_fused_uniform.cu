@@ -26,7 +26,7 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include "vector_ops.cuh"
+#include "cg_device.cuh"
 
 namespace dpp {
 
@@ -62,6 +62,7 @@ struct FArgs {
   const double* S;           // scalar slot of the solver (null in plain-apply mode)
   const double* dtab;        // [2][8] reciprocal diagonal per boundary class bx*4 + by*2 + bz
   int dom_lo, dom_hi;        // local plane 0 / n[0]-1 lies on the domain boundary (else it is a ghost plane)
+  FoldArgs fold;             // <p,Ap> reduction epilogue run by the last CTA
 };
 
 __device__ __forceinline__ int bstart(int t, int n, int nt) { return (int)(((long long)t * n) / nt); }
@@ -98,6 +99,8 @@ struct __align__(128) Smem {
   unsigned long long mbar[RING];
   double red[TY];
   double dtab[16];
+  double fin[kFinishSmem];
+  int last_flag;
 };
 
 // FUSED = true : CG iteration kernel (p = dinv r + beta p_old formed on chip, deferred x update, p stored)
@@ -360,6 +363,8 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
       for (int w = 0; w < TY; ++w) t += sm.red[w];
       s.dot_partials[blockIdx.x] = t;
     }
+    if (FUSED && s.fold.enabled && last_block_arrives(s.fold.counter, gridDim.x, &sm.last_flag))
+      finish_reduction(s.dot_partials, (int)gridDim.x, 1, s.fold.S, s.fold.hist, s.fold.post, 0, s.fold.ipc, sm.fin);
   }
 }
 
@@ -385,31 +390,12 @@ struct RArgs {
   unsigned sh_k, sh_j;
   int dom_lo, dom_hi;
   long long plane;           // padded plane (doubles)
+  int zero_class[2];         // field f: every domain-boundary node is a Dirichlet node (and no other)
+  FoldArgs fold;
   IpcHalo halo;              // peer residual vectors: boundary planes are stored there as well
 };
 
-constexpr int VT = 256;
 constexpr int UNROLL = 4;
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-__device__ __forceinline__ double block_sum(double v, double* sm) {
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) sm[wid] = v;
-  __syncthreads();
-  double t = 0.0;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int w = 0; w < VT / 32; ++w) t += sm[w];
-  }
-  return t;
-}
 
 __device__ __forceinline__ void push_halo(const RArgs& a, int f, long long q, double v) {
   if (a.halo.peer_r[0] != nullptr && q < a.ob + a.plane)
@@ -431,8 +417,9 @@ __device__ __forceinline__ int node_class(const RArgs& a, unsigned q) {
 
 template <bool INIT>
 __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
-  __shared__ double sm[VT / 32];
+  __shared__ double sm[kFinishSmem];
   __shared__ double tab[16];
+  __shared__ int last_flag;
   if (!INIT && a.S[S_REASON] != 0.0) return;
   if (threadIdx.x < 16) tab[threadIdx.x] = (threadIdx.x < 8 * a.nf) ? a.dtab[threadIdx.x] : 1.0;
   __syncthreads();
@@ -445,6 +432,7 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
   double* rf = a.r + (long long)f * a.field;
   const double* wf = INIT ? nullptr : a.w + (long long)f * a.field;
   const double* tf = tab + f * 8;
+  const bool zc = a.zero_class[f] != 0;
   double srz = 0.0, szz = 0.0;
   long long q = a.ob + b + threadIdx.x;
   const long long qe = a.ob + (e > b ? e : b);
@@ -458,24 +446,26 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       double rn = rv[u];
+      const int cls = node_class(a, (unsigned)(q + u * VT));
       if (!INIT) {
-        rn = fma(-alpha, wv[u], rv[u]);
+        rn = (zc && cls) ? 0.0 : fma(-alpha, wv[u], rv[u]);
         rf[q + u * VT] = rn;
         push_halo(a, f, q + u * VT, rn);
       }
-      const double zv = tf[node_class(a, (unsigned)(q + u * VT))] * rn;
+      const double zv = tf[cls] * rn;
       srz = fma(rn, zv, srz);
       szz = fma(zv, zv, szz);
     }
   }
   for (; q < qe; q += VT) {
     double rn = rf[q];
+    const int cls = node_class(a, (unsigned)q);
     if (!INIT) {
-      rn = fma(-alpha, wf[q], rn);
+      rn = (zc && cls) ? 0.0 : fma(-alpha, wf[q], rn);
       rf[q] = rn;
       push_halo(a, f, q, rn);
     }
-    const double zv = tf[node_class(a, (unsigned)q)] * rn;
+    const double zv = tf[cls] * rn;
     srz = fma(rn, zv, srz);
     szz = fma(zv, zv, szz);
   }
@@ -486,6 +476,8 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
     a.partials[bb * 2] = t0;
     a.partials[bb * 2 + 1] = t1;
   }
+  if (a.fold.enabled && last_block_arrives(a.fold.counter, gridDim.x * gridDim.y, &last_flag))
+    finish_reduction(a.partials, (int)(gridDim.x * gridDim.y), 2, a.fold.S, a.fold.hist, a.fold.post, 0, a.fold.ipc, sm);
 }
 
 // boundary planes of r -> the neighbours' ghost planes (start of a solve)
@@ -563,10 +555,29 @@ __global__ void k_fix_rows_padded(const FixPArgs a) {
   }
 }
 
+// count[0] = constrained nodes in the interior, count[1] = unconstrained nodes on the domain boundary
+__global__ void __launch_bounds__(VT) k_classify_mask(RArgs a, const uint8_t* __restrict__ mask, long long n_nodes,
+                                                       unsigned nk_u, unsigned long long mag_nk, unsigned sh_nk,
+                                                       unsigned long long* __restrict__ count) {
+  unsigned long long c0 = 0, c1 = 0;
+  for (long long n = (long long)blockIdx.x * VT + threadIdx.x; n < n_nodes; n += (long long)gridDim.x * VT) {
+    const unsigned row = (unsigned)(((unsigned long long)(unsigned)n * mag_nk) >> sh_nk);
+    const unsigned k = (unsigned)n - row * nk_u;
+    const int cls = node_class(a, row * a.pitch + k);
+    const bool m = mask[n] != 0;
+    c0 += (m && cls == 0);
+    c1 += (!m && cls != 0);
+  }
+  if (c0) atomicAdd(&count[0], c0);
+  if (c1) atomicAdd(&count[1], c1);
+}
+
 // reciprocal diagonal per boundary class; same expression as k_diag_structured (apply_structured.cu)
-__global__ void k_dinv_table(GridDesc g, Coef c, int nf, int jacobi, double* __restrict__ tab) {
+__global__ void k_dinv_table(GridDesc g, Coef c, int nf, int jacobi, int zc0, int zc1, double* __restrict__ tab) {
   const int t = threadIdx.x;
   if (t >= 8 * nf) return;
+  // full-boundary Dirichlet field: every boundary class is a constrained row -> z = 0, p = 0 there
+  if (((t >> 3) ? zc1 : zc0) && (t & 7)) { tab[t] = 0.0; return; }
   if (!jacobi) { tab[t] = 1.0; return; }
   const int f = t >> 3, bx = (t >> 2) & 1, by = (t >> 1) & 1, bz = t & 1;
   // centre entries: row 0 of the assembled 1-D matrices is a domain-boundary row; on a uniform axis an
@@ -623,6 +634,10 @@ struct FusedState {
   long long bc_count[2] = {0, 0};
   long long bc_cap[2] = {0, 0};
   int64_t bc_gen[2] = {-1, -1};   // ctx->bc_gen the padded ids were derived from
+  int bc_full[2] = {0, 0};        // Dirichlet set of the field == all domain-boundary nodes (class-mask mode)
+  int64_t bc_full_gen[2] = {-1, -1};
+  int bc_full_dom[2] = {-1, -1};  // dom_lo + 2*dom_hi the classification was made for
+  unsigned long long* d_count = nullptr;
   bool attr_set = false;
 };
 
@@ -633,6 +648,7 @@ void cg_fused_destroy(dpp_context* ctx) {
     if (b) cudaFree(b);
   for (int32_t* b : F->bc_pad)
     if (b) cudaFree(b);
+  if (F->d_count) cudaFree(F->d_count);
   delete F;
   ctx->fused = nullptr;
 }
@@ -697,6 +713,17 @@ static int fused_state(dpp_context* ctx, FusedState** out) {
   return DPP_OK;
 }
 
+static FoldArgs fold_args(dpp_context* ctx, int slot, int post, int counter) {
+  FoldArgs f{};
+  f.enabled = (ctx->world == 1 || comm_ipc_ready(ctx)) ? 1 : 0;
+  f.counter = ctx->d_counters + counter;
+  f.S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
+  f.hist = hist_device(ctx, slot);
+  f.post = post;
+  f.ipc = comm_ipc_reduce_args(ctx);
+  return f;
+}
+
 static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, const Coef& c, int pin_idx, double* pout,
                         int slot, const double* dtab, bool want_dot, int* n_partial_blocks) {
   const GridDesc& g = ctx->grid;
@@ -721,6 +748,7 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
   s.S = fused ? ctx->d_scalars + (size_t)slot * S_SLOT_SIZE : nullptr;
   s.dtab = dtab;
   s.dom_lo = ctx->dom_lo; s.dom_hi = ctx->dom_hi;
+  if (fused) s.fold = fold_args(ctx, slot, POST_CG_PAP, 0);
   s.ntk = ((g.n[2] + 1) / 2 + TK / 2 - 1) / (TK / 2);   // tiles hold <= TK/2 column pairs
   s.ntj = (g.n[1] + TJ - 1) / TJ;
   const int tiles = s.ntk * s.ntj;
@@ -758,7 +786,30 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
   return DPP_OK;
 }
 
-static int make_rargs(dpp_context* ctx, FusedState* F, int nf, int slot, const double* dtab, RArgs* out) {
+// is the Dirichlet set of mask field `fl` exactly the set of domain-boundary nodes?  (decided once per BC
+// change with a device pass over the mask; then boundary classes double as the row/column mask)
+static int classify_bcs(dpp_context* ctx, FusedState* F, int fl, const RArgs& geom) {
+  const int dom = ctx->dom_lo + 2 * ctx->dom_hi;
+  if (F->bc_full_gen[fl] == ctx->bc_gen[fl] && F->bc_full_dom[fl] == dom) return DPP_OK;
+  if (!F->d_count) DPP_CHECK(dev_alloc(ctx, &F->d_count, 2));
+  DPP_CUDA(cudaMemsetAsync(F->d_count, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  unsigned long long mag; unsigned sh;
+  magic_div((unsigned)F->nk, &mag, &sh);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((ctx->n_nodes + VT - 1) / VT, (long long)ctx->sm_count * 8));
+  k_classify_mask<<<blocks, VT, 0, ctx->stream>>>(geom, ctx->d_mask + (size_t)fl * ctx->n_nodes, ctx->n_nodes,
+                                                  (unsigned)F->nk, mag, sh, F->d_count);
+  ctx->launches++;
+  unsigned long long h[2] = {1, 1};
+  DPP_CUDA(cudaMemcpyAsync(h, F->d_count, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  F->bc_full[fl] = (h[0] == 0 && h[1] == 0 && getenv("DPP_NO_CLASS_MASK") == nullptr) ? 1 : 0;
+  F->bc_full_gen[fl] = ctx->bc_gen[fl];
+  F->bc_full_dom[fl] = dom;
+  return DPP_OK;
+}
+
+static int make_rargs(dpp_context* ctx, FusedState* F, int nf, int slot, const double* dtab, RArgs* out,
+                      const int* fld = nullptr, int post = POST_NONE) {
   const GridDesc& g = ctx->grid;
   const long long uplane = (long long)g.n[1] * g.n[2];
   RArgs a{};
@@ -778,6 +829,13 @@ static int make_rargs(dpp_context* ctx, FusedState* F, int nf, int slot, const d
   a.dom_hi = ctx->dom_hi;
   a.plane = F->plane;
   a.halo = comm_ipc_halo(ctx);
+  if (fld != nullptr) {
+    for (int f = 0; f < nf; ++f) {
+      DPP_CHECK(classify_bcs(ctx, F, fld[f], a));
+      a.zero_class[f] = F->bc_full[fld[f]];
+    }
+    a.fold = fold_args(ctx, slot, post, 1);
+  }
   *out = a;
   return DPP_OK;
 }
@@ -789,8 +847,13 @@ static int r_blocks(const dpp_context* ctx, const RArgs& a) {
   return (int)std::max(1LL, std::min(std::min(want, cap), (long long)kMaxPartialBlocks / 2));
 }
 
-int cg_fused_table(dpp_context* ctx, const Coef& c, int nf, int pc_type, double* d_tab) {
-  k_dinv_table<<<1, 16, 0, ctx->stream>>>(ctx->grid, c, nf, pc_type == DPP_PC_JACOBI ? 1 : 0, d_tab);
+int cg_fused_table(dpp_context* ctx, const Coef& c, int nf, int pc_type, const int* fld, double* d_tab) {
+  FusedState* F = nullptr;
+  DPP_CHECK(fused_state(ctx, &F));
+  RArgs geom{};
+  DPP_CHECK(make_rargs(ctx, F, nf, 0, d_tab, &geom, fld));
+  k_dinv_table<<<1, 16, 0, ctx->stream>>>(ctx->grid, c, nf, pc_type == DPP_PC_JACOBI ? 1 : 0, geom.zero_class[0],
+                                          nf == 2 ? geom.zero_class[1] : 0, d_tab);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   return DPP_OK;
@@ -811,39 +874,45 @@ int cg_fused_begin(dpp_context* ctx, int nf, const double* b) {
   return DPP_OK;
 }
 
-int cg_fused_rz_init(dpp_context* ctx, int nf, int slot, const double* dtab, int* nblocks) {
+// <r,z>, <z,z> of the initial residual + POST_CG_INIT
+int cg_fused_rz_init(dpp_context* ctx, int nf, const int* fld, int slot, const double* dtab) {
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
   RArgs a{};
-  DPP_CHECK(make_rargs(ctx, F, nf, slot, dtab, &a));
+  DPP_CHECK(make_rargs(ctx, F, nf, slot, dtab, &a, fld, POST_CG_INIT));
   dim3 grid(r_blocks(ctx, a), nf);
   k_cg_r_update<true><<<grid, VT, 0, ctx->stream>>>(a);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
-  *nblocks = grid.x * grid.y;
+  if (!a.fold.enabled) DPP_CHECK(reduce_partials(ctx, grid.x * grid.y, 2, slot, POST_CG_INIT));
   return DPP_OK;
 }
 
-int cg_fused_r_update(dpp_context* ctx, int nf, int slot, const double* dtab, int* nblocks) {
+// r -= alpha w (+ halo push), <r,z>, <z,z> + POST_CG_RZ
+int cg_fused_r_update(dpp_context* ctx, int nf, const int* fld, int slot, const double* dtab) {
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
   RArgs a{};
-  DPP_CHECK(make_rargs(ctx, F, nf, slot, dtab, &a));
+  DPP_CHECK(make_rargs(ctx, F, nf, slot, dtab, &a, fld, POST_CG_RZ));
   dim3 grid(r_blocks(ctx, a), nf);
   k_cg_r_update<false><<<grid, VT, 0, ctx->stream>>>(a);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
-  *nblocks = grid.x * grid.y;
+  if (!a.fold.enabled) DPP_CHECK(reduce_partials(ctx, grid.x * grid.y, 2, slot, POST_CG_RZ));
   return DPP_OK;
 }
 
 // iteration `it` (0-based count of applies so far): w = A p, p = dinv.*r + beta*p_prev, x += alpha_prev p_prev
-int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const int* fld, int slot, const double* dtab,
-                   int* n_partial_blocks) {
+int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const int* fld, int slot, const double* dtab) {
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
   const int pin = 1 + (int)(it & 1), pout = 1 + (int)((it + 1) & 1);
-  DPP_CHECK(launch_apply(ctx, F, nf, true, c, pin, F->buf[pout], slot, dtab, true, n_partial_blocks));
+  int nb = 0;
+  DPP_CHECK(launch_apply(ctx, F, nf, true, c, pin, F->buf[pout], slot, dtab, true, &nb));
+  if (!(ctx->world == 1 || comm_ipc_ready(ctx))) DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
+  bool all_class_masked = true;
+  for (int f = 0; f < nf; ++f) all_class_masked = all_class_masked && F->bc_full_gen[fld[f]] == ctx->bc_gen[fld[f]] && F->bc_full[fld[f]];
+  if (all_class_masked) return DPP_OK;   // constrained rows never leave zero: no row fix-up needed
   // row elimination: w = p on constrained rows (identity rows of A_bc)
   const PadGeom g = pad_geom(ctx, F, nf);
   FixPArgs fx{};

@@ -87,7 +87,6 @@ struct Comm {
   double* r_peer[2] = {nullptr, nullptr}; // mapped residual vectors of rank-1 / rank+1
   long long r_peer_field[2] = {0, 0}, r_peer_ghost_off[2] = {0, 0};
   std::vector<void*> mapped;              // everything opened with cudaIpcOpenMemHandle
-  unsigned long long seq = 0;
 };
 
 namespace {
@@ -192,14 +191,17 @@ int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n) {
 
 bool comm_ipc_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc; }
 
-IpcReduce comm_ipc_next_reduce(dpp_context* ctx) {
+IpcReduce comm_ipc_reduce_args(dpp_context* ctx) {
   Comm* C = ctx->comm;
   IpcReduce a{};
+  a.world = 1;
+  if (!C || !C->ipc) return a;
   a.local = C->mbox;
   for (int r = 0; r < ctx->world; ++r) a.peer[r] = (r == ctx->rank) ? C->mbox : C->mbox_peer[r];
   a.rank = ctx->rank;
   a.world = ctx->world;
-  a.seq = ++C->seq;
+  // the sequence counter lives behind the mailbox entries; it advances only when an exchange really runs
+  a.seq_dev = reinterpret_cast<unsigned long long*>(C->mbox + 2 * kMaxIpcRanks * kMboxEntry);
   return a;
 }
 
@@ -288,8 +290,8 @@ int dpp_comm_ipc_export(dpp_handle ctx, void* blob_out) {
                   ? dpp::cg_fused_r_buffer(ctx, &field, &plane) : nullptr;
   if (r != nullptr) {
     if (!C->mbox) {
-      DPP_CHECK(dpp::dev_alloc(ctx, &C->mbox, 2 * dpp::kMaxIpcRanks * dpp::kMboxEntry));
-      DPP_CUDA(cudaMemset(C->mbox, 0, sizeof(double) * 2 * dpp::kMaxIpcRanks * dpp::kMboxEntry));
+      DPP_CHECK(dpp::dev_alloc(ctx, &C->mbox, 2 * dpp::kMaxIpcRanks * dpp::kMboxEntry + 2));
+      DPP_CUDA(cudaMemset(C->mbox, 0, sizeof(double) * (2 * dpp::kMaxIpcRanks * dpp::kMboxEntry + 2)));
     }
     const long long uplane = (long long)ctx->grid.n[1] * ctx->grid.n[2];
     if (cudaIpcGetMemHandle(&b.r_handle, r) == cudaSuccess && cudaIpcGetMemHandle(&b.mbox_handle, C->mbox) == cudaSuccess) {

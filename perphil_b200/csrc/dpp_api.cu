@@ -99,6 +99,8 @@ int dpp_create(dpp_handle* h, int device, int dim, int degree, int64_t n_nodes, 
     DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_scalars, dpp::kNumScalars));
     DPP_CUDA(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * dpp::kNumScalars, ctx->stream));
     DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_dtab, 32));
+    DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_counters, 4));
+    DPP_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned) * 4, ctx->stream));
     DPP_CUDA(cudaMallocHost((void**)&ctx->h_scalars, sizeof(double) * dpp::kNumScalars));
     std::memset(ctx->h_scalars, 0, sizeof(double) * dpp::kNumScalars);
     DPP_CHECK(dpp::structured_detect_and_setup(ctx, cnm, coords, ccnm));
@@ -123,7 +125,7 @@ void dpp_destroy(dpp_handle ctx) {
   dpp::comm_destroy(ctx);
   void* ptrs[] = {ctx->d_cnm, ctx->d_coords, ctx->ccnm_alias ? nullptr : ctx->d_ccnm, ctx->d_tables, ctx->d_adj_ptr,
                   ctx->d_adj_cell, ctx->d_adj_loc, ctx->d_cell_geom, ctx->d_mask, ctx->d_g, ctx->d_solution, ctx->d_diag,
-                  ctx->d_partials, ctx->d_scalars, ctx->d_dtab, ctx->d_hist[0], ctx->d_hist[1], ctx->d_premask, ctx->d_bc_nodes[0], ctx->d_bc_nodes[1], ctx->d_bc_vals};
+                  ctx->d_partials, ctx->d_scalars, ctx->d_dtab, ctx->d_counters, ctx->d_hist[0], ctx->d_hist[1], ctx->d_premask, ctx->d_bc_nodes[0], ctx->d_bc_nodes[1], ctx->d_bc_vals};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);

@@ -137,6 +137,7 @@ struct dpp_context {
   double* d_partials = nullptr;   // [kMaxPartialBlocks * kMaxDotWidth]
   double* d_scalars = nullptr;    // device scalar block
   double* h_scalars = nullptr;    // pinned mirror
+  unsigned* d_counters = nullptr; // arrival counters of the folded reductions [4]
   double* d_dtab = nullptr;       // [2 slots][16] reciprocal-diagonal class tables of the fused CG
   double* d_hist[2] = {nullptr, nullptr};  // residual history per solver slot
   int hist_cap[2] = {0, 0};
@@ -210,8 +211,16 @@ constexpr int kMboxEntry = 8;      // doubles per mailbox entry: 7 values + sequ
 struct IpcReduce {                 // kernel argument of the mailbox allreduce
   double* local;                   // [2 slots][world][kMboxEntry]
   double* peer[kMaxIpcRanks];      // the same array of every rank (peer[rank] == local)
-  int rank, world;
-  unsigned long long seq;
+  int rank, world;                 // world == 1: no exchange
+  unsigned long long* seq_dev;     // own device counter: number of exchanges executed so far
+};
+struct FoldArgs {                  // reduction epilogue folded into the producing kernel ("last block done")
+  int enabled;
+  unsigned* counter;               // self-resetting arrival counter
+  double* S;                       // scalar slot (read-write)
+  double* hist;
+  int post;
+  IpcReduce ipc;
 };
 struct IpcHalo {                   // kernel argument of the halo push (padded layout)
   double* peer_r[2];               // lower / upper neighbour's residual vector (null: none)
@@ -219,7 +228,7 @@ struct IpcHalo {                   // kernel argument of the halo push (padded l
   long long peer_ghost_off[2];     // offset of the ghost plane that mirrors my boundary plane
 };
 bool comm_ipc_ready(const dpp_context* ctx);
-IpcReduce comm_ipc_next_reduce(dpp_context* ctx);   // bumps the sequence number
+IpcReduce comm_ipc_reduce_args(dpp_context* ctx);   // world == 1 when the mailbox path is not active
 IpcHalo comm_ipc_halo(const dpp_context* ctx);
 // residual buffer registration (cg_fused_uniform.cu owns the memory)
 double* cg_fused_r_buffer(dpp_context* ctx, long long* field, long long* plane);

@@ -162,23 +162,19 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
     // two kernels per iteration (cg_fused_uniform.cu): p, x updates live inside the apply kernel
     const Coef coef = op.nf == 2 ? dpp_coef(ctx) : block_coef(ctx, op.row, op.col);
     double* dtab = ctx->d_dtab + (size_t)slot * 16;
-    DPP_CHECK(cg_fused_table(ctx, coef, op.nf, pc.type, dtab));
+    const int fld[2] = {op.nf == 2 ? 0 : op.row, 1};
+    DPP_CHECK(cg_fused_table(ctx, coef, op.nf, pc.type, fld, dtab));
     DPP_CHECK(cg_fused_begin(ctx, op.nf, b));
     DPP_CHECK(cg_fused_halo_r(ctx, op.nf, false, slot));
-    int nb = 0;
-    DPP_CHECK(cg_fused_rz_init(ctx, op.nf, slot, dtab, &nb));
-    DPP_CHECK(reduce_partials(ctx, nb, 2, slot, POST_CG_INIT));
+    DPP_CHECK(cg_fused_rz_init(ctx, op.nf, fld, slot, dtab));
     DPP_CHECK(scalars_fetch(ctx, slot));
-    const int fld[2] = {op.nf == 2 ? 0 : op.row, 1};
     const int every = std::max(1, check_every);
     long long kk = 0;
     while (h[S_REASON] == 0.0) {
       for (int k = 0; k < every; ++k, ++kk) {
-        DPP_CHECK(cg_fused_apply(ctx, op.nf, coef, kk, fld, slot, dtab, &nb));
+        DPP_CHECK(cg_fused_apply(ctx, op.nf, coef, kk, fld, slot, dtab));
         ctx->krylov->apply_count++;
-        DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
-        DPP_CHECK(cg_fused_r_update(ctx, op.nf, slot, dtab, &nb));
-        DPP_CHECK(reduce_partials(ctx, nb, 2, slot, POST_CG_RZ));
+        DPP_CHECK(cg_fused_r_update(ctx, op.nf, fld, slot, dtab));
         DPP_CHECK(cg_fused_halo_r(ctx, op.nf, true, slot));
       }
       DPP_CHECK(scalars_fetch(ctx, slot));
@@ -562,13 +558,14 @@ int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply
   DPP_CHECK(scalars_init(ctx, slot, 1e-8, 1e-12, 1e4, 1 << 30, 0));
   double* hs = ctx->h_scalars + (size_t)slot * S_SLOT_SIZE;
   hs[S_ITS] = 1.0; hs[S_RZ] = 1.0; hs[S_RZ_OLD] = 2.0; hs[S_PAP] = 1.0; hs[S_ALPHA] = 1e-3; hs[S_XPEND] = 1.0;
-  hs[S_RTOL] = 1e-8; hs[S_ATOL] = 1e-12; hs[S_DTOL] = 1e4; hs[S_MAXIT] = (double)(1 << 30);
+  hs[S_RTOL] = 0.0; hs[S_ATOL] = 0.0; hs[S_DTOL] = 1e300; hs[S_MAXIT] = 1e18;
+  hs[S_RNORM0] = 1e300; hs[S_TTOL] = 0.0;  // the folded convergence test never fires while timing
   DPP_CUDA(cudaMemcpyAsync(S, hs, sizeof(double) * S_SLOT_SIZE, cudaMemcpyHostToDevice, ctx->stream));
   DPP_CUDA(cudaStreamSynchronize(ctx->stream));
   const Coef coef = dpp_coef(ctx);
   double* dtab = ctx->d_dtab;
-  DPP_CHECK(cg_fused_table(ctx, coef, 2, DPP_PC_JACOBI, dtab));
   const int fld[2] = {0, 1};
+  DPP_CHECK(cg_fused_table(ctx, coef, 2, DPP_PC_JACOBI, fld, dtab));
   cudaEvent_t e0, e1;
   DPP_CUDA(cudaEventCreate(&e0));
   DPP_CUDA(cudaEventCreate(&e1));
@@ -578,8 +575,8 @@ int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply
   for (int pass = 0; pass < 3; ++pass) {
     for (int i = -warmup; i < reps; ++i) {
       if (i == 0) DPP_CUDA(cudaEventRecord(e0, ctx->stream));
-      if (pass == 0) DPP_CHECK(cg_fused_apply(ctx, 2, coef, i + warmup, fld, slot, dtab, &nb));
-      else if (pass == 1) DPP_CHECK(cg_fused_r_update(ctx, 2, slot, dtab, &nb));
+      if (pass == 0) DPP_CHECK(cg_fused_apply(ctx, 2, coef, i + warmup, fld, slot, dtab));
+      else if (pass == 1) DPP_CHECK(cg_fused_r_update(ctx, 2, fld, slot, dtab));
       else DPP_CHECK(cg_fused_plain_apply(ctx, 2, coef, true, &nb));
     }
     DPP_CUDA(cudaEventRecord(e1, ctx->stream));

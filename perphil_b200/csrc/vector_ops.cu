@@ -3,35 +3,13 @@
 #include <algorithm>
 #include <cmath>
 
-#include "vector_ops.cuh"
+#include "cg_device.cuh"
 
 namespace dpp {
 
 namespace {
 
-constexpr int VT = 256;   // threads per block
 constexpr int UNROLL = 4;
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// block-wide sum in a fixed order; result valid in thread 0
-__device__ __forceinline__ double block_sum(double v, double* sm /*[VT/32]*/) {
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) sm[wid] = v;
-  __syncthreads();
-  double t = 0.0;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int w = 0; w < VT / 32; ++w) t += sm[w];
-  }
-  return t;
-}
 
 struct Chunk {
   long long begin, end;  // element range inside the field (absolute index into the array)
@@ -44,52 +22,6 @@ __device__ __forceinline__ Chunk my_chunk(const VecLayout& L) {
   const long long e = b + per < nown ? b + per : nown;
   const long long base = (long long)blockIdx.y * L.stride + L.ob;
   return Chunk{base + b, base + (e > b ? e : b)};
-}
-
-__device__ void apply_post(double* S, double* hist, int post) {
-  // executed by one thread after the reduction values are in S[S_TMP..]
-  if (post == POST_CG_PAP) {
-    if (S[S_REASON] != 0.0) return;  // the apply was a no-op: partials are stale
-    const double pap = S[S_TMP];
-    S[S_PAP] = pap;
-    if (!(pap > 0.0)) {
-      S[S_REASON] = (pap == pap) ? DPP_DIVERGED_INDEFINITE_MAT : DPP_DIVERGED_NANORINF;
-      S[S_XPEND] = 0.0;
-    } else {
-      S[S_ALPHA] = S[S_RZ] / pap;
-      S[S_XPEND] = 1.0;
-    }
-    return;
-  }
-  if (post == POST_CG_INIT || post == POST_CG_RZ) {
-    if (S[S_REASON] != 0.0) return;
-    const double rz = S[S_TMP], zz = S[S_TMP + 1];
-    const double rnorm = sqrt(zz);
-    int its;
-    if (post == POST_CG_INIT) {
-      its = 0;
-      S[S_RZ_OLD] = 1.0;
-      S[S_RNORM0] = rnorm;
-      const double t = S[S_RTOL] * rnorm;
-      S[S_TTOL] = t > S[S_ATOL] ? t : S[S_ATOL];
-    } else {
-      its = (int)S[S_ITS] + 1;
-      S[S_RZ_OLD] = S[S_RZ];
-    }
-    S[S_RZ] = rz;
-    S[S_ZZ] = zz;
-    S[S_RNORM] = rnorm;
-    S[S_ITS] = (double)its;
-    if (hist != nullptr && its < (int)S[S_HISTCAP]) hist[its] = rnorm;
-    // KSPConvergedDefault
-    double reason = 0.0;
-    if (!(rnorm == rnorm) || isinf(rnorm)) reason = DPP_DIVERGED_NANORINF;
-    else if (rnorm <= S[S_TTOL]) reason = (rnorm < S[S_ATOL]) ? DPP_CONVERGED_ATOL : DPP_CONVERGED_RTOL;
-    else if (rnorm >= S[S_DTOL] * S[S_RNORM0]) reason = DPP_DIVERGED_DTOL;
-    else if (rz == 0.0) reason = DPP_CONVERGED_ATOL;
-    else if (its >= (int)S[S_MAXIT]) reason = DPP_DIVERGED_ITS;
-    S[S_REASON] = reason;
-  }
 }
 
 __global__ void __launch_bounds__(VT) k_reduce_partials(const double* __restrict__ partials, int nblocks, int width,
@@ -107,56 +39,12 @@ __global__ void __launch_bounds__(VT) k_reduce_partials(const double* __restrict
 
 __global__ void k_post_only(double* S, double* hist, int post) { apply_post(S, hist, post); }
 
-// Local reduction + all-reduce over the ranks' mailboxes (peer memory, NVLink) + post-op, one block.
-// Every rank writes its partial sums into slot (seq & 1) of EVERY rank's mailbox, flag last; then
-// waits until all ranks' entries of this sequence number have arrived in its own mailbox and adds them
-// in rank order -- the same order everywhere, so all ranks hold bit-identical sums.  Two slots are
-// enough: a rank can run at most one reduction ahead of the slowest one.
+// Local reduction + all-reduce over the ranks' mailboxes + post-op, one block (cg_device.cuh)
 __global__ void __launch_bounds__(VT) k_reduce_partials_ipc(const double* __restrict__ partials, int nblocks, int width,
                                                              double* S, double* hist, int post, int out_offset,
                                                              IpcReduce ipc) {
-  __shared__ double sm[VT / 32];
-  __shared__ double vals[kMboxEntry];
-  __shared__ int timed_out;
-  if (threadIdx.x == 0) timed_out = 0;
-  for (int w = 0; w < width; ++w) {
-    double v = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += VT) v += partials[(size_t)b * width + w];
-    const double t = block_sum(v, sm);
-    if (threadIdx.x == 0) vals[w] = t;
-  }
-  __syncthreads();
-  const int slot = (int)(ipc.seq & 1ull);
-  const double tag = (double)ipc.seq;
-  if (threadIdx.x < ipc.world) {
-    double* dst = ipc.peer[threadIdx.x] + ((size_t)slot * ipc.world + ipc.rank) * kMboxEntry;
-    for (int w = 0; w < width; ++w) dst[w] = vals[w];
-    __threadfence_system();   // also orders the halo stores of the preceding kernel before the flag
-    *reinterpret_cast<volatile double*>(dst + kMboxEntry - 1) = tag;
-    const volatile double* src = ipc.local + ((size_t)slot * ipc.world + threadIdx.x) * kMboxEntry;
-    const long long t0 = clock64();
-    while (src[kMboxEntry - 1] != tag) {
-      if (clock64() - t0 > 60000000000LL) {  // ~30 s: a peer died; report instead of hanging the GPU
-        timed_out = 1;
-        break;
-      }
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (timed_out) {
-      S[S_REASON] = (double)DPP_DIVERGED_COMM_TIMEOUT;
-    } else {
-      for (int w = 0; w < width; ++w) {
-        double t = 0.0;
-        for (int r = 0; r < ipc.world; ++r)
-          t += reinterpret_cast<const volatile double*>(ipc.local)[((size_t)slot * ipc.world + r) * kMboxEntry + w];
-        S[S_TMP + out_offset + w] = t;
-      }
-      apply_post(S, hist, post);
-    }
-  }
+  __shared__ double sm[kFinishSmem];
+  finish_reduction(partials, nblocks, width, S, hist, post, out_offset, ipc, sm);
 }
 
 __global__ void __launch_bounds__(VT) k_axpby(VecLayout L, double a, const double* x, double b, double* y) {
@@ -389,7 +277,7 @@ int reduce_partials(dpp_context* ctx, int nblocks, int width, int slot, PostOp p
   const bool dist = ctx->world > 1;
   if (dist && comm_ipc_ready(ctx) && width < kMboxEntry) {
     k_reduce_partials_ipc<<<1, VT, 0, ctx->stream>>>(ctx->d_partials, nblocks, width, S, hist_device(ctx, slot), (int)post,
-                                                     out_offset, comm_ipc_next_reduce(ctx));
+                                                     out_offset, comm_ipc_reduce_args(ctx));
     ctx->launches++;
     DPP_CUDA(cudaGetLastError());
     return DPP_OK;
