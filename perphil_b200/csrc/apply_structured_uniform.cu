@@ -308,6 +308,7 @@ int structured_fix_rows(dpp_context* ctx, int nf, const int* fld, double* const*
                         int identity, const double* skip_flag) {
   FixArgs fx{};
   for (int f = 0; f < nf; ++f) {
+    if (fld[f] < 0) continue;  // this field has no row elimination
     fx.nodes[f] = ctx->d_bc_nodes[fld[f]];
     fx.count[f] = ctx->n_bc[fld[f]];
     fx.y[f] = y[f];

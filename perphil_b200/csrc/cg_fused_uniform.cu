@@ -764,6 +764,15 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
     s.nseg = 0;
     nctas = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count * 2, total / 8));
   }
+  if (const char* e = getenv("DPP_FUSED_SCHED")) {  // measurement override: "p" persistent, "<n>" segments
+    if (e[0] == 'p') {
+      s.nseg = 0;
+      nctas = (int)std::max<long long>(1, std::min<long long>(ctx->sm_count * 2, total / 4));
+    } else if (atoi(e) > 0 && (long long)tiles * atoi(e) <= kMaxPartialBlocks) {
+      s.nseg = std::min(atoi(e), nown);
+      nctas = tiles * s.nseg;
+    }
+  }
   if (!F->attr_set) {
     DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<2>)));
     DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));

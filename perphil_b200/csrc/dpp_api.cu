@@ -104,7 +104,7 @@ int dpp_create(dpp_handle* h, int device, int dim, int degree, int64_t n_nodes, 
     DPP_CUDA(cudaMallocHost((void**)&ctx->h_scalars, sizeof(double) * dpp::kNumScalars));
     std::memset(ctx->h_scalars, 0, sizeof(double) * dpp::kNumScalars);
     DPP_CHECK(dpp::structured_detect_and_setup(ctx, cnm, coords, ccnm));
-    ctx->family = (ctx->structured_ok && degree == 1) ? DPP_KERNEL_STRUCTURED : DPP_KERNEL_GENERAL;
+    ctx->family = ctx->structured_ok ? DPP_KERNEL_STRUCTURED : DPP_KERNEL_GENERAL;
     if (ctx->family == DPP_KERNEL_GENERAL) DPP_CHECK(dpp::general_setup(ctx, cnm));
     DPP_CUDA(cudaStreamSynchronize(ctx->stream));
     return DPP_OK;
@@ -159,7 +159,7 @@ int dpp_force_kernel_family(dpp_handle ctx, int family) {
   if (!ctx) return DPP_ERR_INVALID;
   cudaSetDevice(ctx->device);
   if (family == DPP_KERNEL_STRUCTURED) {
-    if (!ctx->structured_ok || ctx->degree != 1) {
+    if (!ctx->structured_ok) {
       ctx->set_error("structured kernel family unavailable for this mesh");
       return DPP_ERR_INVALID;
     }

@@ -157,7 +157,7 @@ constexpr int kNumScalars = 256;
 // of neighbouring tiles then hit in L2 -- a fully persistent partition loses that, measured: 2x DRAM
 // reads).  Cost model: rounds of `capacity` resident CTAs x (planes per segment + 2 redundant planes +
 // prologue); returns the segment count with the smallest cost.
-inline int choose_x_segments(int tiles, int nown, int capacity, int max_ctas) {
+inline int choose_x_segments(int tiles, int nown, int capacity, int max_ctas, int redundant = 2) {
   int best = 1;
   long long best_cost = -1;
   for (int nseg = 1; nseg <= nown; ++nseg) {
@@ -165,7 +165,7 @@ inline int choose_x_segments(int tiles, int nown, int capacity, int max_ctas) {
     const int len = (nown + nseg - 1) / nseg;
     if (len < 4 && nseg > 1) break;
     const long long rounds = ((long long)tiles * nseg + capacity - 1) / capacity;
-    const long long cost = rounds * (len + 2 + 2);
+    const long long cost = rounds * (len + redundant + 2);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nseg; }
   }
   return best;

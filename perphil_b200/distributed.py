@@ -40,8 +40,13 @@ class Slab:
     def n_local_planes(self) -> int:
         return self.local_plane_hi - self.local_plane_lo
 
-    def owned_local_planes(self):
-        return self.plane_lo - self.local_plane_lo, self.plane_hi - self.local_plane_lo
+    def owned_local_planes(self, degree: int = 1):
+        """[begin, end) of the owned node planes of a degree-p space in local plane numbering.  The slab
+        is cut at vertex planes; a degree-p space has p node planes per cell layer, the rank owns node
+        planes [p*plane_lo, p*plane_hi) of the global lattice (clipped to the p*nx + 1 planes there are)."""
+        p = degree
+        hi = min(p * self.plane_hi, p * self.nx + 1)
+        return p * (self.plane_lo - self.local_plane_lo), hi - p * self.local_plane_lo
 
 
 def make_slab(rank: int, size: int, nx: int) -> Slab:
@@ -58,20 +63,27 @@ def make_slab(rank: int, size: int, nx: int) -> Slab:
     return Slab(rank, size, nx, lo, hi, llo, lhi)
 
 
-def halo_lists(slab: Slab, plane_nodes: int):
+def halo_lists(slab: Slab, plane_nodes: int, degree: int = 1):
     """[(peer, send_local_nodes, recv_local_nodes)] for one scalar field (both fields use the same
-    lists).  Local node id = (global_plane - local_plane_lo) * plane_nodes + in_plane_index."""
+    lists).  Local node id = (global_node_plane - p*local_plane_lo) * plane_nodes + in_plane_index.
+    Degree p: rows of an owned vertex plane reach p node planes down and up, rows of the other planes
+    stay inside their cell layer, so the rank needs the p node planes below its first owned one and the
+    single (vertex) node plane above its last owned one."""
     out = []
+    p = degree
     base = np.arange(plane_nodes, dtype=np.int64)
 
-    def plane(gp):
-        return ((gp - slab.local_plane_lo) * plane_nodes + base).astype(np.int32)
+    def planes(g0, g1):  # global node planes [g0, g1)
+        gp = np.arange(g0, g1, dtype=np.int64)
+        return ((gp[:, None] - p * slab.local_plane_lo) * plane_nodes + base[None, :]).ravel().astype(np.int32)
 
     if slab.rank > 0 and slab.plane_lo > 0:
-        # lower neighbour owns plane_lo-1 (my lower ghost) and needs my first owned plane
-        out.append((slab.rank - 1, plane(slab.plane_lo), plane(slab.plane_lo - 1)))
+        # lower neighbour owns the p node planes below p*plane_lo (my lower ghosts) and needs my first owned plane
+        out.append((slab.rank - 1, planes(p * slab.plane_lo, p * slab.plane_lo + 1),
+                    planes(p * slab.plane_lo - p, p * slab.plane_lo)))
     if slab.rank < slab.size - 1 and slab.plane_hi <= slab.nx:
-        out.append((slab.rank + 1, plane(slab.plane_hi - 1), plane(slab.plane_hi)))
+        out.append((slab.rank + 1, planes(p * slab.plane_hi - p, p * slab.plane_hi),
+                    planes(p * slab.plane_hi, p * slab.plane_hi + 1)))
     return out
 
 
@@ -159,13 +171,12 @@ class SlabComm:
         slab = space_data.slab
         if slab is None or self.size == 1:
             return
-        if space_data.degree != 1:
-            raise NotImplementedError("slab-partitioned runs are built for degree-1 spaces")
+        degree = int(space_data.degree)
         plane_nodes = int(np.prod(V.grid_nodes[1:]))
         uid = self.broadcast_bytes(nccl_unique_id() if self.rank == 0 else None, 128)
-        ob, oe = slab.owned_local_planes()
+        ob, oe = slab.owned_local_planes(degree)
         handle.comm_init(self.rank, self.size, uid, ob * plane_nodes, oe * plane_nodes)
-        for peer, send, recv in halo_lists(slab, plane_nodes):
+        for peer, send, recv in halo_lists(slab, plane_nodes, degree):
             handle.comm_add_neighbor(peer, send, recv)
         # peer-memory fast path (CUDA IPC over NVLink): exchange the handles of every rank's residual vector
         # and mailbox; the library falls back to NCCL by itself if any rank cannot take part

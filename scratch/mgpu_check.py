@@ -7,8 +7,9 @@ from perphil_b200.distributed import SlabComm
 comm = SlabComm.from_env()
 torch.cuda.set_device(comm.device)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+DEG = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 def problem(c):
-    mesh = pb.UnitCubeMesh(N, N, N, comm=c); _, V = pb.create_function_spaces(mesh); W = V * V
+    mesh = pb.UnitCubeMesh(N, N, N, comm=c); _, V = pb.create_function_spaces(mesh, pressure_deg=DEG); W = V * V
     prm = pb.DPPParameters(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
     _, p1, _, p2 = pb.exact_expressions_3d(mesh, prm)
     return mesh, V, W, prm, [pb.DirichletBC(W.sub(0), p1, "on_boundary"), pb.DirichletBC(W.sub(1), p2, "on_boundary")]
@@ -21,8 +22,8 @@ for preset in ("B200_CG_JACOBI_PARAMS", "B200_GMRES_JACOBI_PARAMS", "B200_GMRES_
     m1, V1, W1, prm1, bcs1 = problem(None)
     ref = fn(W1, prm1, bcs1, solver_parameters=getattr(pb, preset))
     slab = mesh.slab
-    pn = (N + 1) ** 2
-    lo, hi = slab.local_plane_lo * pn, slab.local_plane_hi * pn
+    pn = (DEG * N + 1) ** 2
+    lo, hi = DEG * slab.local_plane_lo * pn, (DEG * (slab.local_plane_hi - 1) + 1) * pn
     err = 0.0
     for f in range(2):
         a = sol.solution.sub(f).dat.data; b = ref.solution.sub(f).dat.data[lo:hi]

@@ -26,22 +26,31 @@ def test_partition_covers_planes_once(size, nx):
     assert owned == list(range(nx + 1))
 
 
-@pytest.mark.parametrize("size,nx", [(2, 8), (4, 16), (8, 256)])
-def test_halo_lists_pair_up(size, nx):
+@pytest.mark.parametrize("degree", [1, 2])
+@pytest.mark.parametrize("size,nx", [(2, 8), (4, 16), (8, 256), (8, 192), (3, 7)])
+def test_halo_lists_pair_up(size, nx, degree):
     plane_nodes = 7
+    p = degree
     slabs = [make_slab(r, size, nx) for r in range(size)]
-    lists = [halo_lists(s, plane_nodes) for s in slabs]
+    lists = [halo_lists(s, plane_nodes, degree) for s in slabs]
+    # owned node planes of the degree-p lattice cover [0, p*nx] exactly once
+    owned = np.zeros(p * nx + 1, int)
+    for s in slabs:
+        ob, oe = s.owned_local_planes(degree)
+        owned[p * s.local_plane_lo + ob: p * s.local_plane_lo + oe] += 1
+        assert 0 <= ob < oe <= p * (s.local_plane_hi - s.local_plane_lo - 1) + 1
+    assert np.all(owned == 1)
     for r, s in enumerate(slabs):
         for peer, send, recv in lists[r]:
             back = [x for x in lists[peer] if x[0] == r]
             assert len(back) == 1
             _, psend, precv = back[0]
             # what I send is what the peer receives, in global numbering
-            gl = lambda sl, loc: loc + sl.local_plane_lo * plane_nodes
+            gl = lambda sl, loc: loc + p * sl.local_plane_lo * plane_nodes
             assert np.array_equal(gl(s, send), gl(slabs[peer], precv))
             assert np.array_equal(gl(s, recv), gl(slabs[peer], psend))
             # sends are owned, receives are ghosts
-            ob, oe = s.owned_local_planes()
+            ob, oe = s.owned_local_planes(degree)
             assert np.all((send >= ob * plane_nodes) & (send < oe * plane_nodes))
             assert np.all((recv < ob * plane_nodes) | (recv >= oe * plane_nodes))
 

@@ -448,3 +448,50 @@ def test_fused_cg_kernel_timer_runs():
     # the timer scribbles on the work vectors only: a solve afterwards is unaffected
     sol = pb.solve_dpp(W, p, bcs, solver_parameters=pb.B200_CG_JACOBI_PARAMS)
     assert sol.iteration_number == 31
+
+
+# ---------------------------------------------------------------------------------------------
+# structured Q2 kernel (csrc/apply_structured_q2.cu)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cells", [(3, 4, 5), (6, 5), (8, 8, 8), (17, 3, 21), (1, 1, 1), (40, 37), (2, 9, 20)])
+@pytest.mark.parametrize("bc", ["manufactured", "none"])
+def test_apply_structured_q2(cells, bc):
+    err, h = _apply_case(cells, 2, bc, None)
+    assert h.info().kernel_family == L.KERNEL_STRUCTURED
+    assert err < APPLY_TOL
+    # the two kernel families agree on Q2 as well
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(2 * h.n_nodes)
+    ys = h.apply(x)
+    h.force_kernel_family(L.KERNEL_GENERAL)
+    assert rel_err(h.apply(x), ys) < APPLY_TOL
+
+
+def test_q2_diagonal_and_block_operators():
+    W, p, bcs, osys = make_problem((4, 5, 3), 2)
+    h = configured_handle(W, p, bcs)
+    assert rel_err(h.diagonal(), osys.A_bc.diagonal()) < 1e-13
+
+
+@pytest.mark.parametrize("cells", [(4, 4, 4), (6, 7, 5), (12, 12)])
+def test_q2_cg_jacobi_iteration_parity(cells):
+    W, p, bcs, osys = make_problem(cells, 2)
+    ref = orc.solve_dpp_oracle(osys, "cg", "jacobi")
+    sol = pb.solve_dpp(W, p, bcs, solver_parameters={**pb.B200_CG_JACOBI_PARAMS, "b200_history": 4096})
+    info = pb.last_solve_info()
+    assert pb.handle_for(W).info().kernel_family == L.KERNEL_STRUCTURED
+    assert sol.iteration_number == ref.iteration_number
+    assert np.allclose(info.history, ref.history, rtol=1e-6)
+    u = np.concatenate([sol.solution.sub(0).dat.data, sol.solution.sub(1).dat.data])
+    assert rel_err(u, ref.u) < 1e-9
+
+
+def test_q2_block_picard_config4_shape():
+    """BASELINE configs[3] at a size the oracle reaches: Q2 hexes, scale-splitting Picard, 6 outer iterations."""
+    W, p, bcs, osys = make_problem((6, 6, 6), 2)
+    ref = orc.picard_block_oracle(osys)
+    sol = pb.solve_dpp_nonlinear(W, p, bcs, solver_parameters=pb.B200_PICARD_SPLIT_PARAMS)
+    assert its_close(sol.iteration_number, ref.iteration_number)
+    u = np.concatenate([sol.solution.sub(0).dat.data, sol.solution.sub(1).dat.data])
+    assert rel_err(u, ref.u) < 1e-7
