@@ -265,7 +265,7 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"3D hex Q1 {N}^3 monolithic DPP, matrix-free Jacobi-CG rtol 1e-8, manufactured BCs "
                                f"(BASELINE configs[2]); {ndof} DoF; inputs 10x L2, no flush needed",
-                   "preset": "B200_CG_JACOBI_PARAMS", "iterations": its, "parallelism": f"slab x{world}" + (" peer-memory halo + mailbox allreduce" if h.info().peer_memory else (" NCCL" if world > 1 else "")),
+                   "preset": "B200_CG_JACOBI_PARAMS", "iterations": its, "parallelism": f"slab x{world}" + (" peer-memory halo + mailbox allreduce" if h.info().peer_memory == 3 else (" NCCL" if world > 1 else "")),
                    "kernel_family": "structured" if structured else "general"},
         "iterations": its, "residual_error": sol.residual_error, "wall_ms_per_step": wall_ms,
         "tts_mdofs": ndof / (ms * 1e-3) / 1e6,

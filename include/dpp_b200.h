@@ -148,6 +148,9 @@ int dpp_comm_add_neighbor(dpp_handle h, int peer, int64_t n_send, const int32_t*
 int dpp_comm_ipc_blob_size(void);
 int dpp_comm_ipc_export(dpp_handle h, void* blob_out);
 int dpp_comm_ipc_import(dpp_handle h, const void* blobs_all_ranks);
+/* back to the NCCL path (the host layer calls it on every rank when any rank's import did not succeed:
+ * dpp_info.peer_memory must agree across ranks; bit 0 = mailbox all-reduce, bit 1 = halo push) */
+int dpp_comm_ipc_disable(dpp_handle h);
 
 /* ---- operator ------------------------------------------------------------------------------- */
 

@@ -66,6 +66,7 @@ _PROTOTYPES = {
     "dpp_comm_ipc_blob_size": (C.c_int, []),
     "dpp_comm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dpp_comm_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dpp_comm_ipc_disable": (C.c_int, [C.c_void_p]),
     "dpp_apply_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dpp_apply_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dpp_get_diagonal_host": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -111,6 +111,9 @@ class DppHandle:
         buf = C.create_string_buffer(raw, len(raw))
         self._check(self._lib.dpp_comm_ipc_import(self._h, buf), "dpp_comm_ipc_import")
 
+    def comm_ipc_disable(self) -> None:
+        self._check(self._lib.dpp_comm_ipc_disable(self._h), "dpp_comm_ipc_disable")
+
     # -- operator
     def apply(self, x: np.ndarray, assembled: bool = False) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)

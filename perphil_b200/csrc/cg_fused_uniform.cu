@@ -997,7 +997,7 @@ int cg_fused_halo_r(dpp_context* ctx, int nf, bool after_update, int slot) {
   if (ctx->world <= 1) return DPP_OK;
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
-  if (comm_ipc_ready(ctx)) {
+  if (comm_ipc_halo_ready(ctx)) {
     if (after_update) return DPP_OK;
     // every rank must have finished writing its own r (ghost rows included) before neighbours store into
     // it: a zero-width mailbox reduction is the barrier; the push is then fenced by the next reduction

@@ -74,14 +74,15 @@ struct IpcBlob {  // what every rank publishes (POD; all-gathered by the host la
   cudaIpcMemHandle_t mbox_handle;
   int64_t field, plane;      // padded strides of the residual vector (doubles)
   int32_t i_begin, i_end;    // owned local planes
-  int32_t rank, valid;
+  int32_t rank, valid;       // valid: bit 0 mailbox handle, bit 1 residual-vector handle
 };
 
 struct Comm {
   ncclComm_t comm = nullptr;
   std::vector<Neighbor> nbrs;
   // peer-memory fast path
-  bool ipc = false;
+  bool ipc = false;                       // mailbox all-reduce active
+  bool ipc_halo = false;                  // halo push into the neighbours' residual vectors active
   double* mbox = nullptr;                 // own mailbox [2][world][kMboxEntry]
   double* mbox_peer[kMaxIpcRanks] = {};   // mapped mailboxes of the other ranks
   double* r_peer[2] = {nullptr, nullptr}; // mapped residual vectors of rank-1 / rank+1
@@ -190,6 +191,7 @@ int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n) {
 }
 
 bool comm_ipc_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc; }
+bool comm_ipc_halo_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc && ctx->comm->ipc_halo; }
 
 IpcReduce comm_ipc_reduce_args(dpp_context* ctx) {
   Comm* C = ctx->comm;
@@ -208,7 +210,7 @@ IpcReduce comm_ipc_reduce_args(dpp_context* ctx) {
 IpcHalo comm_ipc_halo(const dpp_context* ctx) {
   IpcHalo h{};
   const Comm* C = ctx->comm;
-  if (C && C->ipc)
+  if (C && C->ipc && C->ipc_halo)
     for (int s = 0; s < 2; ++s) {
       h.peer_r[s] = C->r_peer[s];
       h.peer_field[s] = C->r_peer_field[s];
@@ -285,23 +287,26 @@ int dpp_comm_ipc_export(dpp_handle ctx, void* blob_out) {
   memset(&b, 0, sizeof(b));
   b.rank = ctx->rank;
   dpp::Comm* C = ctx->comm;
-  long long field = 0, plane = 0;
-  double* r = (C && ctx->world > 1 && ctx->world <= dpp::kMaxIpcRanks && !getenv("DPP_NO_IPC"))
-                  ? dpp::cg_fused_r_buffer(ctx, &field, &plane) : nullptr;
-  if (r != nullptr) {
+  if (C && ctx->world > 1 && ctx->world <= dpp::kMaxIpcRanks && !getenv("DPP_NO_IPC")) {
     if (!C->mbox) {
       DPP_CHECK(dpp::dev_alloc(ctx, &C->mbox, 2 * dpp::kMaxIpcRanks * dpp::kMboxEntry + 2));
       DPP_CUDA(cudaMemset(C->mbox, 0, sizeof(double) * (2 * dpp::kMaxIpcRanks * dpp::kMboxEntry + 2)));
     }
-    const long long uplane = (long long)ctx->grid.n[1] * ctx->grid.n[2];
-    if (cudaIpcGetMemHandle(&b.r_handle, r) == cudaSuccess && cudaIpcGetMemHandle(&b.mbox_handle, C->mbox) == cudaSuccess) {
-      b.field = field;
-      b.plane = plane;
-      b.i_begin = (int32_t)(ctx->owned_begin / uplane);
-      b.i_end = (int32_t)(ctx->owned_end / uplane);
-      b.valid = 1;
-    } else {
-      cudaGetLastError();
+    if (cudaIpcGetMemHandle(&b.mbox_handle, C->mbox) == cudaSuccess) b.valid |= 1;
+    else cudaGetLastError();
+    long long field = 0, plane = 0;
+    double* r = dpp::cg_fused_r_buffer(ctx, &field, &plane);   // only the fused (uniform Q1) path has one
+    if (r != nullptr && (b.valid & 1)) {
+      const long long uplane = (long long)ctx->grid.n[1] * ctx->grid.n[2];
+      if (cudaIpcGetMemHandle(&b.r_handle, r) == cudaSuccess) {
+        b.field = field;
+        b.plane = plane;
+        b.i_begin = (int32_t)(ctx->owned_begin / uplane);
+        b.i_end = (int32_t)(ctx->owned_end / uplane);
+        b.valid |= 2;
+      } else {
+        cudaGetLastError();
+      }
     }
   }
   memcpy(blob_out, &b, sizeof(b));
@@ -313,10 +318,14 @@ int dpp_comm_ipc_import(dpp_handle ctx, const void* blobs) {
   cudaSetDevice(ctx->device);
   dpp::Comm* C = ctx->comm;
   C->ipc = false;
+  C->ipc_halo = false;
   const dpp::IpcBlob* B = static_cast<const dpp::IpcBlob*>(blobs);
   if (ctx->world > dpp::kMaxIpcRanks) return DPP_OK;
-  for (int r = 0; r < ctx->world; ++r)
-    if (!B[r].valid || B[r].rank != r) return DPP_OK;  // some rank cannot take part: keep the NCCL path
+  bool all_r = true;
+  for (int r = 0; r < ctx->world; ++r) {
+    if (!(B[r].valid & 1) || B[r].rank != r) return DPP_OK;  // some rank cannot take part: keep the NCCL path
+    all_r = all_r && (B[r].valid & 2);
+  }
   for (int r = 0; r < ctx->world; ++r) {
     if (r == ctx->rank) continue;
     void* m = nullptr;
@@ -327,7 +336,8 @@ int dpp_comm_ipc_import(dpp_handle ctx, const void* blobs) {
     C->mapped.push_back(m);
     C->mbox_peer[r] = static_cast<double*>(m);
   }
-  for (int s = 0; s < 2; ++s) {
+  C->ipc = true;
+  for (int s = 0; s < 2 && all_r; ++s) {
     const int peer = s == 0 ? ctx->rank - 1 : ctx->rank + 1;
     if (peer < 0 || peer >= ctx->world) continue;
     void* m = nullptr;
@@ -343,7 +353,13 @@ int dpp_comm_ipc_import(dpp_handle ctx, const void* blobs) {
     C->r_peer_ghost_off[s] = (s == 0 ? (long long)B[peer].i_end : (long long)B[peer].i_begin - 1) * B[peer].plane;
     if (C->r_peer_ghost_off[s] < 0) return DPP_OK;
   }
-  C->ipc = true;
+  C->ipc_halo = all_r;
+  return DPP_OK;
+}
+
+int dpp_comm_ipc_disable(dpp_handle ctx) {
+  if (!ctx) return DPP_ERR_INVALID;
+  if (ctx->comm) ctx->comm->ipc = ctx->comm->ipc_halo = false;
   return DPP_OK;
 }
 

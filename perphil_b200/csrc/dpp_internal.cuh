@@ -227,7 +227,8 @@ struct IpcHalo {                   // kernel argument of the halo push (padded l
   long long peer_field[2];         // their padded field stride
   long long peer_ghost_off[2];     // offset of the ghost plane that mirrors my boundary plane
 };
-bool comm_ipc_ready(const dpp_context* ctx);
+bool comm_ipc_ready(const dpp_context* ctx);        // mailbox all-reduce
+bool comm_ipc_halo_ready(const dpp_context* ctx);   // + halo push into the neighbours' residual vectors
 IpcReduce comm_ipc_reduce_args(dpp_context* ctx);   // world == 1 when the mailbox path is not active
 IpcHalo comm_ipc_halo(const dpp_context* ctx);
 // residual buffer registration (cg_fused_uniform.cu owns the memory)

@@ -182,6 +182,9 @@ class SlabComm:
         # and mailbox; the library falls back to NCCL by itself if any rank cannot take part
         if self._backend == "nccl":
             handle.comm_ipc_import(self.all_gather_bytes(handle.comm_ipc_export()))
+            modes = self.all_gather_bytes(bytes([handle.info().peer_memory]))
+            if len(set(modes)) != 1:   # every rank must run the same protocol
+                handle.comm_ipc_disable()
 
     def destroy(self):
         if self._dist is not None and self._dist.is_initialized():
