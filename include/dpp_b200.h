@@ -119,6 +119,15 @@ int dpp_get_info(dpp_handle h, dpp_info* info);
  * set_params/set_dirichlet. */
 int dpp_force_kernel_family(dpp_handle h, int family);
 
+/* Optional numbering map.  The kernels are fastest on lexicographically numbered tensor grids; Firedrake
+ * numbers the same lattice arbitrarily (DMPlex order).  The host layer may therefore
+ * create the handle on a lexicographically RE-numbered copy of the mesh and register the map here: from
+ * then on every HOST-facing node list and vector (dpp_set_dirichlet, dpp_apply_host,
+ * dpp_get_diagonal_host, dpp_solve's u_host) is in the caller's numbering, node u being stored internally
+ * at user_to_internal[u].  Device-pointer calls and dpp_get_csr_host stay in internal numbering.
+ * Single-GPU handles only. */
+int dpp_set_numbering(dpp_handle h, const int32_t* user_to_internal_host);
+
 /* DPPParameters (models/dpp/parameters.py:5-53): float(k1), float(k2), float(beta), float(mu). */
 int dpp_set_params(dpp_handle h, double k1, double k2, double beta, double mu);
 

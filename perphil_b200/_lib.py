@@ -59,6 +59,7 @@ _PROTOTYPES = {
     "dpp_last_error": (C.c_char_p, [C.c_void_p]),
     "dpp_get_info": (C.c_int, [C.c_void_p, C.POINTER(DppInfo)]),
     "dpp_force_kernel_family": (C.c_int, [C.c_void_p, C.c_int]),
+    "dpp_set_numbering": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dpp_set_params": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]),
     "dpp_set_dirichlet": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "dpp_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64]),

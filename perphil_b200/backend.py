@@ -51,6 +51,32 @@ class DppHandle:
             msg = self._lib.dpp_last_error(None).decode()
             self._h = C.c_void_p()
             raise DppError(f"dpp_create failed ({rc}): {msg}")
+        self._perm = None   # user -> internal node map (set_numbering)
+
+    @classmethod
+    def from_mesh_arrays(cls, dim: int, degree: int, cell_node_map: np.ndarray, node_coords: np.ndarray,
+                         vertex_coords: np.ndarray, coord_cell_node_map: np.ndarray, n_nodes: Optional[int] = None,
+                         device: int = 0, renumber: bool = True) -> "DppHandle":
+        """Handle for an arbitrarily numbered mesh.  If the mesh is geometrically a rectilinear tensor grid
+        (perphil_b200.lattice) it is created on the lexicographically re-numbered mesh, so that the
+        structured kernels serve it, and the numbering map is registered: every method of this class keeps
+        speaking the caller's numbering."""
+        from .lattice import detect_lattice
+
+        lat = detect_lattice(dim, degree, cell_node_map, node_coords, vertex_coords, coord_cell_node_map) if renumber else None
+        if lat is None or lat.is_identity:
+            return cls(dim, degree, cell_node_map, vertex_coords, coord_cell_node_map, n_nodes=n_nodes, device=device)
+        h = cls(dim, degree, lat.cell_node_map, lat.vertex_coords, lat.cell_vertex_map, n_nodes=lat.perm.size,
+                device=device)
+        h.set_numbering(lat.perm)
+        return h
+
+    def set_numbering(self, user_to_internal: np.ndarray):
+        perm = np.ascontiguousarray(user_to_internal, dtype=np.int32)
+        if perm.size != self.n_nodes:
+            raise ValueError("numbering map must have one entry per node")
+        self._check(self._lib.dpp_set_numbering(self._h, _ptr(perm)), "dpp_set_numbering")
+        self._perm = perm
 
     # -- plumbing
     def _check(self, rc: int, what: str):
@@ -136,6 +162,15 @@ class DppHandle:
         indices = np.empty(nnz.value, dtype=np.int32)
         data = np.empty(nnz.value, dtype=np.float64)
         self._check(self._lib.dpp_get_csr_host(self._h, _ptr(indptr), _ptr(indices), _ptr(data)), "dpp_get_csr_host")
+        if self._perm is not None:
+            # the library assembled on the re-numbered mesh: A_user[u, v] = A_int[perm[u], perm[v]]
+            import scipy.sparse as sp
+
+            n = self.n_nodes
+            pd = np.concatenate([self._perm.astype(np.int64), n + self._perm.astype(np.int64)])
+            A = sp.csr_matrix((data, indices, indptr), shape=(2 * n, 2 * n))[pd][:, pd].tocsr()
+            A.sort_indices()
+            return A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data
         return indptr, indices, data
 
     # -- solve

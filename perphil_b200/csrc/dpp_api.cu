@@ -9,6 +9,7 @@
 
 namespace dpp {
 int krylov_work_vectors(dpp_context* ctx, double** a, double** b);
+double* krylov_scratch_vector(dpp_context* ctx);  // [2*n_nodes], valid after krylov_work_vectors / a solve
 }
 
 static std::string g_create_error;
@@ -36,6 +37,24 @@ __global__ void k_scatter_bc(long long n, const int32_t* __restrict__ nodes, con
   }
 }
 
+__global__ void k_map_ids(long long n, int32_t* __restrict__ ids, const int32_t* __restrict__ perm) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    ids[i] = perm[ids[i]];
+}
+
+// TO_INTERNAL: internal[perm[u]] = user[u] ; else user[u] = internal[perm[u]]   (per field)
+template <bool TO_INTERNAL>
+__global__ void k_permute(long long n, int nf, const int32_t* __restrict__ perm, const double* __restrict__ src,
+                          double* __restrict__ dst) {
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < n; u += (long long)gridDim.x * blockDim.x) {
+    const long long q = perm[u];
+    for (int f = 0; f < nf; ++f) {
+      if (TO_INTERNAL) dst[f * n + q] = src[f * n + u];
+      else dst[f * n + u] = src[f * n + q];
+    }
+  }
+}
+
 int fail_create(dpp_context* ctx, int rc, const std::string& msg) {
   g_create_error = msg.empty() && ctx ? ctx->err : msg;
   if (ctx) dpp_destroy(ctx);
@@ -44,7 +63,54 @@ int fail_create(dpp_context* ctx, int rc, const std::string& msg) {
 
 }  // namespace
 
+namespace dpp {
+int perm_to_internal(dpp_context* ctx, const double* user, double* internal, int nf) {
+  const int blocks = (int)std::min<long long>((ctx->n_nodes + 255) / 256, (long long)ctx->sm_count * 16);
+  k_permute<true><<<blocks, 256, 0, ctx->stream>>>(ctx->n_nodes, nf, ctx->d_perm, user, internal);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+int perm_to_user(dpp_context* ctx, const double* internal, double* user, int nf) {
+  const int blocks = (int)std::min<long long>((ctx->n_nodes + 255) / 256, (long long)ctx->sm_count * 16);
+  k_permute<false><<<blocks, 256, 0, ctx->stream>>>(ctx->n_nodes, nf, ctx->d_perm, internal, user);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+}  // namespace dpp
+
 extern "C" {
+
+int dpp_set_numbering(dpp_handle ctx, const int32_t* map) {
+  if (!ctx || !map) return DPP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->world > 1) {
+    ctx->set_error("dpp_set_numbering: not available on slab-partitioned handles");
+    return DPP_ERR_INVALID;
+  }
+  std::vector<uint8_t> seen((size_t)ctx->n_nodes, 0);
+  for (int64_t i = 0; i < ctx->n_nodes; ++i) {
+    if (map[i] < 0 || map[i] >= ctx->n_nodes || seen[map[i]]) {
+      ctx->set_error("dpp_set_numbering: the map is not a permutation of the nodes");
+      return DPP_ERR_INVALID;
+    }
+    seen[map[i]] = 1;
+  }
+  if (!ctx->d_perm) DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_perm, ctx->n_nodes));
+  DPP_CUDA(cudaMemcpy(ctx->d_perm, map, sizeof(int32_t) * ctx->n_nodes, cudaMemcpyHostToDevice));
+  // Dirichlet data uploaded before the map would be in the wrong numbering: start clean
+  for (int f = 0; f < 2; ++f) {
+    DPP_CUDA(cudaMemsetAsync(ctx->d_mask + f * ctx->n_nodes, 0, ctx->n_nodes, ctx->stream));
+    DPP_CUDA(cudaMemsetAsync(ctx->d_g + f * ctx->n_nodes, 0, sizeof(double) * ctx->n_nodes, ctx->stream));
+    ctx->n_bc[f] = 0;
+    ctx->bc_gen[f]++;
+    ctx->have_bc[f] = false;
+  }
+  ctx->invalidate();
+  dpp::csr_invalidate(ctx);
+  return DPP_OK;
+}
 
 int dpp_create(dpp_handle* h, int device, int dim, int degree, int64_t n_nodes, int64_t n_cells, int nodes_per_cell,
                const int32_t* cnm, int64_t n_coord_nodes, const double* coords, const int32_t* ccnm) {
@@ -125,7 +191,7 @@ void dpp_destroy(dpp_handle ctx) {
   dpp::comm_destroy(ctx);
   void* ptrs[] = {ctx->d_cnm, ctx->d_coords, ctx->ccnm_alias ? nullptr : ctx->d_ccnm, ctx->d_tables, ctx->d_adj_ptr,
                   ctx->d_adj_cell, ctx->d_adj_loc, ctx->d_cell_geom, ctx->d_mask, ctx->d_g, ctx->d_solution, ctx->d_diag,
-                  ctx->d_partials, ctx->d_scalars, ctx->d_dtab, ctx->d_counters, ctx->d_hist[0], ctx->d_hist[1], ctx->d_premask, ctx->d_bc_nodes[0], ctx->d_bc_nodes[1], ctx->d_bc_vals};
+                  ctx->d_partials, ctx->d_scalars, ctx->d_dtab, ctx->d_counters, ctx->d_hist[0], ctx->d_hist[1], ctx->d_premask, ctx->d_bc_nodes[0], ctx->d_bc_nodes[1], ctx->d_bc_vals, ctx->d_perm};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -226,6 +292,10 @@ int dpp_set_dirichlet(dpp_handle ctx, int field, int64_t n, const int32_t* nodes
     DPP_CUDA(cudaMemcpyAsync(d_nodes, nodes, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     DPP_CUDA(cudaMemcpyAsync(ctx->d_bc_vals, values, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4096);
+    if (ctx->d_perm) {  // caller numbering -> internal numbering
+      k_map_ids<<<blocks, 256, 0, ctx->stream>>>(n, d_nodes, ctx->d_perm);
+      ctx->launches++;
+    }
     k_scatter_bc<<<blocks, 256, 0, ctx->stream>>>(n, d_nodes, ctx->d_bc_vals, ctx->d_mask + field * nn, ctx->d_g + field * nn);
     ctx->launches++;
     DPP_CUDA(cudaGetLastError());
@@ -282,10 +352,20 @@ int dpp_apply_host(dpp_handle ctx, const double* x, double* y, int mode) {
   double *dx = nullptr, *dy = nullptr;
   DPP_CHECK(dpp::krylov_work_vectors(ctx, &dx, &dy));
   const size_t bytes = sizeof(double) * 2 * ctx->n_nodes;
-  DPP_CUDA(cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  double* dt = ctx->d_perm ? dpp::krylov_scratch_vector(ctx) : nullptr;
+  if (ctx->d_perm) {
+    DPP_CUDA(cudaMemcpyAsync(dt, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    DPP_CHECK(dpp::perm_to_internal(ctx, dt, dx, 2));
+  } else {
+    DPP_CUDA(cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
   DPP_CUDA(cudaMemsetAsync(dy, 0, bytes, ctx->stream));
   int nb = 0;
   DPP_CHECK(apply_common(ctx, dx, dy, mode, false, &nb));
+  if (ctx->d_perm) {
+    DPP_CHECK(dpp::perm_to_user(ctx, dy, dt, 2));
+    dy = dt;
+  }
   DPP_CUDA(cudaMemcpyAsync(y, dy, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   DPP_CUDA(cudaStreamSynchronize(ctx->stream));
   return DPP_OK;
@@ -299,7 +379,14 @@ int dpp_get_diagonal_host(dpp_handle ctx, double* diag) {
   }
   cudaSetDevice(ctx->device);
   DPP_CHECK(dpp::op_diagonal(ctx));
-  DPP_CUDA(cudaMemcpyAsync(diag, ctx->d_diag, sizeof(double) * 2 * ctx->n_nodes, cudaMemcpyDeviceToHost, ctx->stream));
+  const double* src = ctx->d_diag;
+  if (ctx->d_perm) {
+    double *dx = nullptr, *dy = nullptr;
+    DPP_CHECK(dpp::krylov_work_vectors(ctx, &dx, &dy));
+    DPP_CHECK(dpp::perm_to_user(ctx, ctx->d_diag, dpp::krylov_scratch_vector(ctx), 2));
+    src = dpp::krylov_scratch_vector(ctx);
+  }
+  DPP_CUDA(cudaMemcpyAsync(diag, src, sizeof(double) * 2 * ctx->n_nodes, cudaMemcpyDeviceToHost, ctx->stream));
   DPP_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->diag_valid = false;  // Krylov keeps its own reciprocal; recompute lazily
   return DPP_OK;

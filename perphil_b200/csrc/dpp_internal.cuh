@@ -84,6 +84,8 @@ struct dpp_context {
   int32_t* d_ccnm = nullptr;      // [n_cells*nvc] (aliases d_cnm when degree==1 and same array)
   bool ccnm_alias = false;
 
+  int32_t* d_perm = nullptr;      // optional user -> internal node map (dpp_set_numbering)
+
   // kernel family
   int family = DPP_KERNEL_GENERAL;
   bool structured_ok = false;
@@ -243,6 +245,10 @@ int csr_spmv(dpp_context* ctx, const double* x, double* y, double* dot_partials,
 void csr_invalidate(dpp_context* ctx);
 bool csr_valid(const dpp_context* ctx);
 void csr_destroy(dpp_context* ctx);
+
+// ---- numbering map helpers (dpp_api.cu): internal <-> caller numbering of field-blocked vectors
+int perm_to_internal(dpp_context* ctx, const double* user, double* internal, int nf);
+int perm_to_user(dpp_context* ctx, const double* internal, double* user, int nf);
 
 // ---- krylov.cu
 int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_result* res,

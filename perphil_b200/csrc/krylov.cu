@@ -518,6 +518,8 @@ int ensure_work(dpp_context* ctx) {
 
 }  // namespace
 
+double* krylov_scratch_vector(dpp_context* ctx) { return ctx->krylov ? ctx->krylov->t : nullptr; }
+
 int krylov_work_vectors(dpp_context* ctx, double** a, double** b) {
   DPP_CHECK(ensure_work(ctx));
   *a = ctx->krylov->p;
@@ -666,7 +668,12 @@ int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_r
   DPP_CHECK(vec_axpby(ctx, L2, 1.0, K->x, 1.0, ctx->d_solution));
   DPP_CHECK(halo(ctx, ctx->d_solution, 2));  // ghost planes of the returned vector are consistent
   if (u_host) {
-    DPP_CUDA(cudaMemcpyAsync(u_host, ctx->d_solution, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    const double* src = ctx->d_solution;
+    if (ctx->d_perm) {  // hand the solution back in the caller's numbering
+      DPP_CHECK(perm_to_user(ctx, ctx->d_solution, K->t, 2));
+      src = K->t;
+    }
+    DPP_CUDA(cudaMemcpyAsync(u_host, src, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
   }
   DPP_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms_setup = 0, ms_solve = 0;

@@ -24,6 +24,7 @@ class SpaceData:
     coords: np.ndarray
     coord_cell_node_map: np.ndarray
     slab: object = None
+    node_coords: Optional[np.ndarray] = None   # pressure-node coordinates (real Firedrake meshes): lattice detection
 
 
 def _degree_of(V) -> int:
@@ -68,17 +69,20 @@ def space_data(W) -> SpaceData:
     ccnm = np.asarray(mesh.coordinates.cell_node_map().values, dtype=np.int32)
     cnm = np.asarray(V.cell_node_map().values, dtype=np.int32)
     n_nodes = int(getattr(V, "node_count", None) or V.dim())
+    node_coords = None
     if not isinstance(mesh, _SynthMesh):  # real Firedrake: infer local orders from coordinates
         ccnm = normalise_local_order(ccnm, coords)
         if degree == 1:
             cnm = normalise_local_order(cnm, coords) if cnm is not ccnm else ccnm
+            node_coords = coords
         else:
             import firedrake as fd  # noqa: only reachable with a real Firedrake mesh
 
             Vc = fd.VectorFunctionSpace(mesh, V.ufl_element())
             xn = fd.Function(Vc).interpolate(fd.SpatialCoordinate(mesh)).dat.data_ro
-            cnm = normalise_local_order(cnm, np.asarray(xn))
-    return SpaceData(dim, degree, n_nodes, cnm, coords, ccnm, getattr(mesh, "slab", None))
+            node_coords = np.asarray(xn)
+            cnm = normalise_local_order(cnm, node_coords)
+    return SpaceData(dim, degree, n_nodes, cnm, coords, ccnm, getattr(mesh, "slab", None), node_coords)
 
 
 def bc_data(W, bcs) -> List[Tuple[int, np.ndarray, np.ndarray]]:

@@ -43,7 +43,13 @@ def handle_for(W, device: Optional[int] = None) -> DppHandle:
     sd = space_data(W)
     comm = getattr(W.mesh(), "comm", None)
     dev = device if device is not None else (comm.device if comm is not None else 0)
-    h = DppHandle(sd.dim, sd.degree, sd.cell_node_map, sd.coords, sd.coord_cell_node_map, n_nodes=sd.n_nodes, device=dev)
+    if sd.node_coords is not None:
+        # arbitrarily numbered (Firedrake/DMPlex) mesh: re-number to lexicographic if it is a tensor grid
+        h = DppHandle.from_mesh_arrays(sd.dim, sd.degree, sd.cell_node_map, sd.node_coords, sd.coords,
+                                       sd.coord_cell_node_map, n_nodes=sd.n_nodes, device=dev)
+    else:
+        h = DppHandle(sd.dim, sd.degree, sd.cell_node_map, sd.coords, sd.coord_cell_node_map, n_nodes=sd.n_nodes,
+                      device=dev)
     if comm is not None and comm.size > 1:
         comm.attach(h, sd, W.sub(0))
     try:

@@ -67,8 +67,8 @@ if 2 in want:
     run(f"2: 3D hex Q1 {N2}^3, Jacobi-CG", (N2,) * 3, 1, "B200_CG_JACOBI_PARAMS")
 if 4 in want:
     run(f"4: 3D hex Q2 {N4}^3, block Picard (scale splitting), Jacobi-CG blocks", (N4,) * 3, 2, "B200_PICARD_SPLIT_PARAMS",
-        nonlinear=True, repeats=1)
-    run(f"4: 3D hex Q2 {N4}^3, Jacobi-CG monolithic", (N4,) * 3, 2, "B200_CG_JACOBI_PARAMS", repeats=1)
+        nonlinear=True, repeats=2 if world > 1 else 1)
+    run(f"4: 3D hex Q2 {N4}^3, Jacobi-CG monolithic", (N4,) * 3, 2, "B200_CG_JACOBI_PARAMS", repeats=2 if world > 1 else 1)
 if 5 in want:
     run(f"5: 3D hex Q1 {N5}^3 k2=1e-6 beta=1e2, GMRES + multiplicative fieldsplit", (N5,) * 3, 1,
         "B200_GMRES_FIELDSPLIT_PARAMS", k2=1e-6, beta=1e2, bc="const")

@@ -495,3 +495,47 @@ def test_q2_block_picard_config4_shape():
     assert its_close(sol.iteration_number, ref.iteration_number)
     u = np.concatenate([sol.solution.sub(0).dat.data, sol.solution.sub(1).dat.data])
     assert rel_err(u, ref.u) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------
+# arbitrarily numbered tensor grids (Firedrake/DMPlex order): lattice re-numbering + numbering map
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cells,degree", [((5, 6, 4), 1), ((3, 3, 4), 2), ((7, 9), 1), ((5, 4), 2), ((16, 16, 16), 1)])
+def test_scrambled_numbering_runs_on_structured_kernels(cells, degree):
+    """Everything the handle returns stays in the caller's numbering while the structured (fast) kernel
+    family does the work: apply, diagonal, CSR pattern (bit-exact) and values, Jacobi-CG solve."""
+    from perphil_b200.backend import DppHandle
+    from tests.test_gpu_csr import _full_pattern_reference
+
+    m2 = _shuffled_distorted(cells, degree, 0.0, seed=21)
+    prm = orc.Params(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
+    rng = np.random.default_rng(5)
+    nb = m2.boundary_nodes
+    g1, g2 = rng.standard_normal(nb.size), rng.standard_normal(nb.size)
+    osys = orc.build_system(m2, prm, (nb, g1, nb, g2))
+    h = DppHandle.from_mesh_arrays(m2.dim, degree, m2.cell_node_map, m2.coords, m2.vertex_coords, m2.cell_vertex_map,
+                                   n_nodes=m2.n_nodes)
+    assert h.info().kernel_family == L.KERNEL_STRUCTURED
+    h.set_params(prm.k1, prm.k2, prm.beta, prm.mu)
+    h.set_dirichlet(0, nb, g1)
+    h.set_dirichlet(1, nb, g2)
+    x = rng.standard_normal(osys.n_dof)
+    assert rel_err(h.apply(x), osys.A_bc @ x) < 5e-13
+    assert rel_err(h.diagonal(), osys.A_bc.diagonal()) < 5e-13
+    ref = orc.solve_dpp_oracle(osys, "cg", "jacobi")
+    u, info = h.solve()
+    assert info.iterations == ref.iteration_number
+    assert rel_err(u, ref.u) < 1e-8
+    if np.prod(cells) <= 200:
+        indptr, indices, data = h.assemble_csr()
+        rp, ri, rd = _full_pattern_reference(osys)
+        assert np.array_equal(indptr, rp) and np.array_equal(indices, ri)
+        assert np.abs(data - rd).max() <= 1e-12 * np.abs(rd).max()
+    h.close()
+    # a distorted mesh keeps the general kernels
+    m3 = _shuffled_distorted(cells, degree, 0.3, seed=21)
+    h3 = DppHandle.from_mesh_arrays(m3.dim, degree, m3.cell_node_map, m3.coords, m3.vertex_coords, m3.cell_vertex_map,
+                                    n_nodes=m3.n_nodes)
+    assert h3.info().kernel_family == L.KERNEL_GENERAL
+    h3.close()

@@ -154,3 +154,23 @@ def test_local_order_normalisation():
     for c in range(s2.shape[0]):
         s2[c] = s2[c, rng.permutation(8)]
     assert np.array_equal(normalise_local_order(s2, om.coords), om.cell_node_map)
+
+
+@pytest.mark.parametrize("cells,degree", [((5, 6, 4), 1), ((3, 3, 4), 2), ((7, 9), 1), ((5, 4), 2)])
+def test_lattice_detection_on_scrambled_numbering(cells, degree):
+    """A DMPlex-style arbitrary numbering of a tensor grid is recognised and mapped to lexicographic order."""
+    from perphil_b200.lattice import detect_lattice
+    from tests.test_gpu_parity import _shuffled_distorted
+
+    m = _shuffled_distorted(cells, degree, 0.0, seed=3)
+    lat = detect_lattice(m.dim, degree, m.cell_node_map, m.coords, m.vertex_coords, m.cell_vertex_map)
+    assert lat is not None and not lat.is_identity and lat.cells == tuple(cells)
+    ref = orc.structured_mesh(cells, degree)
+    # node u sits at lexicographic position perm[u]
+    assert np.allclose(ref.coords[lat.perm], m.coords, atol=1e-12)
+    assert np.array_equal(lat.cell_node_map, ref.cell_node_map)
+    assert np.allclose(lat.vertex_coords, ref.vertex_coords)
+    # a lexicographic mesh maps to itself; a distorted one is not a lattice
+    assert detect_lattice(ref.dim, degree, ref.cell_node_map, ref.coords).is_identity
+    d = _shuffled_distorted(cells, degree, 0.3, seed=3)
+    assert detect_lattice(d.dim, degree, d.cell_node_map, d.coords, d.vertex_coords, d.cell_vertex_map) is None
