@@ -190,6 +190,14 @@ int dpp_solve(dpp_handle h, const dpp_options* opt, double* u_host, dpp_result* 
               double* residual_history_host, int32_t history_capacity);
 const double* dpp_solution_dev(dpp_handle h);
 
+/* ---- post-processing: error norms (utils/postprocessing.py:89-124) ---------- */
+
+/* out = { ||p1_h - p1||^2_L2, ||p2_h - p2||^2_L2, |p1_h - p1|^2_H1, |p2_h - p2|^2_H1 } by nq^dim-point Gauss
+ * quadrature over the cells.  u_host [2*n_nodes] (NULL: the solution of the last dpp_solve);
+ * exact_host [2*n_nodes] nodal exact field of the same space, or NULL for the manufactured closed form of
+ * utils/manufactured_solutions.py:39-51 (2-D) / :82-88 (3-D) with the handle's parameters.  Single-GPU. */
+int dpp_error_norms(dpp_handle h, const double* u_host, const double* exact_host, int nq, double* out4);
+
 /* ---- page-locked host buffers for results (full-rate D2H of the solution vector) -------------- */
 int dpp_host_alloc(void** ptr, int64_t bytes);   /* cudaMallocHost */
 int dpp_host_free(void* ptr);

@@ -82,6 +82,7 @@ _PROTOTYPES = {
                                      C.POINTER(C.c_double)]),
     "dpp_kernel_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "dpp_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "dpp_error_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dpp_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "dpp_host_free": (C.c_int, [C.c_void_p]),
 }

@@ -208,6 +208,15 @@ class DppHandle:
                     "dpp_time_cg_kernels")
         return a.value, u.value, m.value
 
+    def error_norms(self, u: Optional[np.ndarray] = None, exact: Optional[np.ndarray] = None, nq: int = 6):
+        """(L2_1, L2_2, H1semi_1, H1semi_2) of u - exact; u None = the last solve's solution, exact None = the
+        manufactured closed form for the handle's parameters."""
+        out = np.zeros(4)
+        uu = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+        ee = None if exact is None else np.ascontiguousarray(exact, dtype=np.float64)
+        self._check(self._lib.dpp_error_norms(self._h, _ptr(uu), _ptr(ee), int(nq), _ptr(out)), "dpp_error_norms")
+        return tuple(float(np.sqrt(v)) for v in out)
+
     def launch_count(self) -> int:
         n = C.c_int64()
         self._check(self._lib.dpp_kernel_launch_count(self._h, C.byref(n)), "dpp_kernel_launch_count")

@@ -479,6 +479,47 @@ int dpp_time_cg_kernels(dpp_handle ctx, int warmup, int reps, double* apply_ms, 
   return dpp::krylov_time_cg_kernels(ctx, warmup, reps, apply_ms, update_ms, matvec_ms);
 }
 
+int dpp_error_norms(dpp_handle ctx, const double* u_host, const double* exact_host, int nq, double* out4) {
+  if (!ctx || !out4) return DPP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_params) {
+    ctx->set_error("dpp_error_norms: call dpp_set_params first");
+    return DPP_ERR_STATE;
+  }
+  if (ctx->world > 1) {
+    ctx->set_error("dpp_error_norms: single-GPU handles only");
+    return DPP_ERR_INVALID;
+  }
+  double *dx = nullptr, *dy = nullptr;
+  DPP_CHECK(dpp::krylov_work_vectors(ctx, &dx, &dy));   // dx: u, dy: exact, scratch: staging for the numbering map
+  double* dt = dpp::krylov_scratch_vector(ctx);
+  const size_t bytes = sizeof(double) * 2 * ctx->n_nodes;
+  const double* du = ctx->d_solution;
+  if (u_host) {
+    if (ctx->d_perm) {
+      DPP_CUDA(cudaMemcpyAsync(dt, u_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      DPP_CHECK(dpp::perm_to_internal(ctx, dt, dx, 2));
+    } else {
+      DPP_CUDA(cudaMemcpyAsync(dx, u_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    du = dx;
+  } else if (!du) {
+    ctx->set_error("dpp_error_norms: no solution on the device yet");
+    return DPP_ERR_STATE;
+  }
+  const double* de = nullptr;
+  if (exact_host) {
+    if (ctx->d_perm) {
+      DPP_CUDA(cudaMemcpyAsync(dt, exact_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      DPP_CHECK(dpp::perm_to_internal(ctx, dt, dy, 2));
+    } else {
+      DPP_CUDA(cudaMemcpyAsync(dy, exact_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    de = dy;
+  }
+  return dpp::error_norms(ctx, du, de, nq, out4);
+}
+
 int dpp_host_alloc(void** ptr, int64_t bytes) {
   if (!ptr || bytes <= 0) return DPP_ERR_INVALID;
   return cudaMallocHost(ptr, (size_t)bytes) == cudaSuccess ? DPP_OK : DPP_ERR_CUDA;

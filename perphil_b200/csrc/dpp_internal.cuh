@@ -250,6 +250,9 @@ void csr_destroy(dpp_context* ctx);
 int perm_to_internal(dpp_context* ctx, const double* user, double* internal, int nf);
 int perm_to_user(dpp_context* ctx, const double* internal, double* user, int nf);
 
+// ---- error_norms.cu
+int error_norms(dpp_context* ctx, const double* d_u, const double* d_exact, int nq, double out[4]);
+
 // ---- krylov.cu
 int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_result* res,
                  double* hist_host, int32_t hist_cap);

@@ -539,3 +539,43 @@ def test_scrambled_numbering_runs_on_structured_kernels(cells, degree):
                                     n_nodes=m3.n_nodes)
     assert h3.info().kernel_family == L.KERNEL_GENERAL
     h3.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# error norms on the GPU (csrc/error_norms.cu) -- SURVEY 8(f) item 1
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("N", [4, 8, 16])
+def test_error_norms_reproduce_convergence_csv(golden, N):
+    """l2_error / h1_seminorm_error of the GPU solution against the manufactured expressions reproduce the
+    accuracy columns the reference stores (convergence.csv, GMRES rows, rtol 1e-8)."""
+    row = next(r for r in golden["convergence_2d"] if r["N"] == N and r["solver"] == "GMRES")
+    mesh = pb.UnitSquareMesh(N, N)
+    _, V = pb.create_function_spaces(mesh)
+    W = V * V
+    prm = pb.DPPParameters(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
+    _, p1, _, p2 = pb.exact_expressions(mesh, prm)
+    bcs = [pb.DirichletBC(W.sub(0), p1, "on_boundary"), pb.DirichletBC(W.sub(1), p2, "on_boundary")]
+    sol = pb.solve_dpp(W, prm, bcs, solver_parameters=pb.B200_GMRES_PARAMS)
+    p1_h, p2_h = pb.split_dpp_solution(sol.solution)
+    got = (pb.l2_error(p1_h, p1), pb.l2_error(p2_h, p2), pb.h1_seminorm_error(p1_h, p1), pb.h1_seminorm_error(p2_h, p2))
+    for v, key in zip(got, ("e1_L2", "e2_L2", "e1_H1s", "e2_H1s")):
+        assert v == pytest.approx(row[key], rel=5e-6)   # GMRES stops at rtol 1e-8: last digits depend on round-off
+
+
+@pytest.mark.parametrize("cells,degree", [((5, 4, 6), 1), ((3, 4, 3), 2), ((7, 5), 2)])
+def test_error_norms_vs_oracle(cells, degree):
+    W, p, bcs, osys = make_problem(cells, degree)
+    h = configured_handle(W, p, bcs)
+    rng = np.random.default_rng(2)
+    u = rng.standard_normal(osys.n_dof)
+    ref = orc.error_norms(osys.mesh, osys.prm, u, nq=5)
+    got = h.error_norms(u, None, 5)
+    assert np.allclose(got, ref, rtol=1e-11)
+    e = rng.standard_normal(osys.n_dof)
+    assert np.allclose(h.error_norms(u, e, 4), orc.error_norms(osys.mesh, osys.prm, u, nq=4, exact=e), rtol=1e-11)
+    # a nodal "exact" field: L2^2 = e^T M e, H1^2 = e^T K e
+    d = u - e
+    n = osys.n_nodes
+    l2 = [np.sqrt(d[f * n:(f + 1) * n] @ (osys.M @ d[f * n:(f + 1) * n])) for f in range(2)]
+    assert np.allclose(h.error_norms(u, e, 3)[:2], l2, rtol=1e-11)

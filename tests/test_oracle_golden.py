@@ -157,3 +157,17 @@ def test_block_picard_h_independent():
         assert sol.iteration_number == 6
         ref = orc.solve_dpp_oracle(s, "preonly", "lu")
         assert np.linalg.norm(sol.u - ref.u) / np.linalg.norm(ref.u) < 1e-8
+
+
+@pytest.mark.parametrize("N", [4, 8, 16, 32])
+def test_error_norms_match_convergence_csv(golden, N):
+    """convergence.csv columns e1_L2, e2_L2, e1_H1s, e2_H1s (MUMPS rows): l2_error / h1_seminorm_error of the
+    direct solution against the manufactured expressions (utils/postprocessing.py:89-124)."""
+    row = next(r for r in golden["convergence_2d"] if r["N"] == N and "MUMPS" in r["solver"])
+    mesh = orc.structured_mesh((N, N), 1)
+    prm = orc.Params(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
+    osys = orc.build_system(mesh, prm, "manufactured")
+    sol = orc.solve_dpp_oracle(osys, "preonly", "lu")
+    e = orc.error_norms(mesh, prm, sol.u, nq=6)
+    for got, key in zip(e, ("e1_L2", "e2_L2", "e1_H1s", "e2_H1s")):
+        assert got == pytest.approx(row[key], rel=2e-7)
