@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <utility>
 
 #include "cg_device.cuh"
 
@@ -87,6 +88,11 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map
       "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// programmatic dependent launch (PDL): let the next kernel of the stream start launching while this one
+// drains, and wait for the previous kernel's results only where they are first needed
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -109,7 +115,7 @@ template <int NF, bool FUSED>
 __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const __grid_constant__ CUtensorMap tm_r,
                                                           const __grid_constant__ CUtensorMap tm_p,
                                                           const __grid_constant__ CUtensorMap tm_x) {
-  if (FUSED && s.S[S_REASON] != 0.0) return;
+  pdl_launch_dependents();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem<NF>& sm = *reinterpret_cast<Smem<NF>*>(smem_raw);
   constexpr int RS = Smem<NF>::RS;
@@ -127,6 +133,8 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     for (int q = 0; q < RING; ++q) mbar_init(mbar0 + 8 * q, 1);
     fence_mbar_init();
   }
+  pdl_wait();  // everything below reads what the previous kernel of the stream produced
+  if (FUSED && s.S[S_REASON] != 0.0) return;
   if (tid < 16) sm.dtab[tid] = (FUSED && tid < 8 * NF) ? s.dtab[tid] : 1.0;
   // scalars of the iteration (device resident; written by the reduction epilogues)
   double beta = 0.0, alpha_prev = 0.0;
@@ -420,6 +428,8 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
   __shared__ double sm[kFinishSmem];
   __shared__ double tab[16];
   __shared__ int last_flag;
+  pdl_launch_dependents();
+  pdl_wait();
   if (!INIT && a.S[S_REASON] != 0.0) return;
   if (threadIdx.x < 16) tab[threadIdx.x] = (threadIdx.x < 8 * a.nf) ? a.dtab[threadIdx.x] : 1.0;
   __syncthreads();
@@ -713,6 +723,23 @@ static int fused_state(dpp_context* ctx, FusedState** out) {
   return DPP_OK;
 }
 
+// launch with programmatic stream serialization allowed (the kernel calls griddepcontrol.wait itself)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = getenv("DPP_NO_PDL") ? 0 : 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static FoldArgs fold_args(dpp_context* ctx, int slot, int post, int counter) {
   FoldArgs f{};
   f.enabled = (ctx->world == 1 || comm_ipc_ready(ctx)) ? 1 : 0;
@@ -783,10 +810,10 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
   dim3 grid(nctas), block(TK, TY);
   const CUtensorMap* T = F->tm[nf - 1];
   if (nf == 2) {
-    if (fused) k_cg_fused_apply<2, true><<<grid, block, sizeof(Smem<2>), ctx->stream>>>(s, T[0], T[pin_idx], T[3]);
+    if (fused) DPP_CUDA(launch_pdl(k_cg_fused_apply<2, true>, grid, block, sizeof(Smem<2>), ctx->stream, s, T[0], T[pin_idx], T[3]));
     else k_cg_fused_apply<2, false><<<grid, block, sizeof(Smem<2>), ctx->stream>>>(s, T[0], T[pin_idx], T[3]);
   } else {
-    if (fused) k_cg_fused_apply<1, true><<<grid, block, sizeof(Smem<1>), ctx->stream>>>(s, T[0], T[pin_idx], T[3]);
+    if (fused) DPP_CUDA(launch_pdl(k_cg_fused_apply<1, true>, grid, block, sizeof(Smem<1>), ctx->stream, s, T[0], T[pin_idx], T[3]));
     else k_cg_fused_apply<1, false><<<grid, block, sizeof(Smem<1>), ctx->stream>>>(s, T[0], T[pin_idx], T[3]);
   }
   ctx->launches++;
@@ -904,7 +931,7 @@ int cg_fused_r_update(dpp_context* ctx, int nf, const int* fld, int slot, const 
   RArgs a{};
   DPP_CHECK(make_rargs(ctx, F, nf, slot, dtab, &a, fld, POST_CG_RZ));
   dim3 grid(r_blocks(ctx, a), nf);
-  k_cg_r_update<false><<<grid, VT, 0, ctx->stream>>>(a);
+  DPP_CUDA(launch_pdl(k_cg_r_update<false>, grid, dim3(VT), 0, ctx->stream, a));
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   if (!a.fold.enabled) DPP_CHECK(reduce_partials(ctx, grid.x * grid.y, 2, slot, POST_CG_RZ));

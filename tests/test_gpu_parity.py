@@ -579,3 +579,17 @@ def test_error_norms_vs_oracle(cells, degree):
     n = osys.n_nodes
     l2 = [np.sqrt(d[f * n:(f + 1) * n] @ (osys.M @ d[f * n:(f + 1) * n])) for f in range(2)]
     assert np.allclose(h.error_norms(u, e, 3)[:2], l2, rtol=1e-11)
+
+
+def test_perf_harness_row_has_the_reference_schema():
+    """experiments.run_perf_once_3d: one CSV row in the column names of petsc_perf_breakdown_3d.csv."""
+    from perphil_b200 import experiments as ex
+
+    row = ex.run_perf_once_3d(8, ex.Approach.CG_JACOBI, repeats=2)
+    assert row["dofs"] == 1458 and row["num_cells"] == 512 and row["iterations"] == 15
+    assert row["time_KSPSolve"] > 0 and row["time_MatMult"] > 0 and row["time_total"] > 0
+    df = ex.run_perf_sweep_3d([4], [ex.Approach.PLAIN_GMRES, ex.Approach.SS_GMRES], repeats=1)
+    assert list(df.columns) == list(ex.CSV_COLUMNS) and len(df) == 2
+    _, V = pb.create_function_spaces(pb.UnitCubeMesh(4, 4, 4))
+    res = ex.solve_on_mesh(V * V, ex.Approach.CG_JACOBI)
+    assert res.iteration_number == 0 and res.fields is not None   # homogeneous default BCs: trivial solution

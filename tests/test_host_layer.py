@@ -174,3 +174,28 @@ def test_lattice_detection_on_scrambled_numbering(cells, degree):
     assert detect_lattice(ref.dim, degree, ref.cell_node_map, ref.coords).is_identity
     d = _shuffled_distorted(cells, degree, 0.3, seed=3)
     assert detect_lattice(d.dim, degree, d.cell_node_map, d.coords, d.vertex_coords, d.cell_vertex_map) is None
+
+
+def test_approach_routing_follows_the_reference_harness():
+    """experiments/iterative_bench.py:31-48,157-188: same enum values where an approach exists in the reference;
+    MUMPS/ILU approaches are refused on the B200 path."""
+    from perphil_b200 import experiments as ex
+
+    assert ex.Approach.PLAIN_GMRES.value == "GMRES"
+    assert ex.Approach.SS_GMRES.value == "Scale-Splitting GMRES"
+    assert ex.Approach.MONOLITHIC_MUMPS.value == "Monolithic LU with MUMPS"
+    p = ex.params_for(ex.Approach.SS_GMRES)
+    assert p["pc_type"] == "fieldsplit" and p["pc_fieldsplit_type"] == "multiplicative" and p[prm.B200_BACKEND_KEY] == "b200"
+    assert ex.params_for("GMRES")["pc_type"] == "none"
+    p["ksp_rtol"] = 0.5
+    assert ex.params_for(ex.Approach.SS_GMRES)["ksp_rtol"] == 1e-8   # a copy is returned
+    for a in (ex.Approach.GMRES_ILU, ex.Approach.SS_GMRES_ILU, ex.Approach.MONOLITHIC_MUMPS):
+        with pytest.raises(NotImplementedError):
+            ex.params_for(a)
+    mp = ex.default_model_params()
+    assert float(mp.k2) == 1e-2 and float(mp.k1) == 1.0
+    mesh = pb.UnitSquareMesh(3, 3)
+    _, V = pb.create_function_spaces(mesh)
+    bcs = ex.default_bcs(V * V)
+    assert len(bcs) == 2 and np.all(bcs[0].values() == 0.0)
+    assert "time_KSPSolve" in ex.CSV_COLUMNS and "time_MatMult" in ex.CSV_COLUMNS
