@@ -60,6 +60,7 @@ struct FArgs {
   double* dot_partials;
   int i_begin, i_end;
   int ntj, ntk, nseg;
+  int j_lo, j_hi, k_lo, k_hi;  // nodes of a plane that are computed (class-mask mode: interior only)
   const double* S;           // scalar slot of the solver (null in plain-apply mode)
   const double* dtab;        // [2][8] reciprocal diagonal per boundary class bx*4 + by*2 + bz
   int dom_lo, dom_hi;        // local plane 0 / n[0]-1 lies on the domain boundary (else it is a ghost plane)
@@ -171,11 +172,12 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     wbeg += run_len;
     const int i_lo = s.i_begin + run_a, i_hi = i_lo + run_len;
     const int tkid = tile % s.ntk, tjid = tile / s.ntk;
-    const int nkp = (nk + 1) >> 1;  // tiles are cut between even columns
-    const int k0 = 2 * bstart(tkid, nkp, s.ntk), k1 = min(nk, 2 * bstart(tkid + 1, nkp, s.ntk));
-    const int j0 = bstart(tjid, nj, s.ntj), j1 = bstart(tjid + 1, nj, s.ntj);
+    // tiles cover the computed node range [j_lo, j_hi) x [k_lo, k_hi); they are cut between even columns
+    const int kp_lo = s.k_lo >> 1, nkp = ((s.k_hi + 1) >> 1) - kp_lo;
+    const int k0 = 2 * (kp_lo + bstart(tkid, nkp, s.ntk)), k1 = min(s.k_hi, 2 * (kp_lo + bstart(tkid + 1, nkp, s.ntk)));
+    const int j0 = s.j_lo + bstart(tjid, s.j_hi - s.j_lo, s.ntj), j1 = s.j_lo + bstart(tjid + 1, s.j_hi - s.j_lo, s.ntj);
     const int jA = j0 + 2 * ty, jB = jA + 1, k = k0 + tx;
-    const bool actA = (jA < j1) && (k < k1), actB = (jB < j1) && (k < k1);
+    const bool actA = (jA < j1) && (k >= s.k_lo) && (k < k1), actB = (jB < j1) && (k >= s.k_lo) && (k < k1);
     const int i_first = i_lo - 1;
     // planes whose p this run stores: its output planes, plus the ghost plane next to the first/last owned one
     const int pw_lo = (i_lo == s.i_begin && s.i_begin > 0) ? i_lo - 1 : i_lo;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     phase ^= 1u << (C);                                                                               \
     double cen[NF][2];                                                                                \
     if (FUSED) {                                                                                      \
-      const bool pbnd = (ip == 0 && s.dom_lo) || (ip == ni - 1 && s.dom_hi);                          \
+      const bool pbnd = ni > 1 && ((ip == 0 && s.dom_lo) || (ip == ni - 1 && s.dom_hi));              \
       const bool pwr = ip >= pw_lo && ip < pw_hi;                                                     \
       const bool xwr = xpend && ip >= i_lo && ip < i_hi;                                              \
       _Pragma("unroll") for (int f = 0; f < NF; ++f) {                                                \
@@ -417,7 +419,7 @@ __device__ __forceinline__ int node_class(const RArgs& a, unsigned q) {
   const unsigned k = q - t * a.pitch;
   const unsigned i = (unsigned)(((unsigned long long)t * a.mag_j) >> a.sh_j);   // t / nj
   const unsigned j = t - i * a.nj;
-  const int bx = ((i == 0 && a.dom_lo) || (i == a.ni - 1 && a.dom_hi)) ? 4 : 0;
+  const int bx = (a.ni > 1 && ((i == 0 && a.dom_lo) || (i == a.ni - 1 && a.dom_hi))) ? 4 : 0;  // dummy axis: no class
   const int by = (j == 0 || j == a.nj - 1) ? 2 : 0;
   const int bz = (k == 0 || k == a.nk - 1) ? 1 : 0;
   return bx + by + bz;
@@ -752,7 +754,7 @@ static FoldArgs fold_args(dpp_context* ctx, int slot, int post, int counter) {
 }
 
 static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, const Coef& c, int pin_idx, double* pout,
-                        int slot, const double* dtab, bool want_dot, int* n_partial_blocks) {
+                        int slot, const double* dtab, bool want_dot, int* n_partial_blocks, bool interior_only = false) {
   const GridDesc& g = ctx->grid;
   const long long uplane = (long long)g.n[1] * g.n[2];
   if (ctx->owned_begin % uplane || ctx->owned_end % uplane) {
@@ -776,8 +778,18 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
   s.dtab = dtab;
   s.dom_lo = ctx->dom_lo; s.dom_hi = ctx->dom_hi;
   if (fused) s.fold = fold_args(ctx, slot, POST_CG_PAP, 0);
-  s.ntk = ((g.n[2] + 1) / 2 + TK / 2 - 1) / (TK / 2);   // tiles hold <= TK/2 column pairs
-  s.ntj = (g.n[1] + TJ - 1) / TJ;
+  s.j_lo = 0; s.j_hi = g.n[1]; s.k_lo = 0; s.k_hi = g.n[2];
+  if (fused && interior_only && g.n[1] >= 3 && g.n[2] >= 3 && (g.n[0] >= 3 || g.n[0] == 1)) {
+    // class-mask mode: every domain-boundary node is a constrained row whose p, w, x stay zero and whose
+    // w is never read -- compute the interior only (at 257^2 planes: 16 x 8 = 128 tiles instead of 153)
+    s.j_lo = 1; s.j_hi = g.n[1] - 1; s.k_lo = 1; s.k_hi = g.n[2] - 1;
+    if (g.n[0] > 1) {  // domain-boundary planes too, as long as the rank keeps at least one plane to compute
+      if (ctx->dom_lo && s.i_begin == 0 && s.i_end - s.i_begin > 1) s.i_begin = 1;
+      if (ctx->dom_hi && s.i_end == g.n[0] && s.i_end - s.i_begin > 1) s.i_end = g.n[0] - 1;
+    }
+  }
+  s.ntk = (((s.k_hi + 1) >> 1) - (s.k_lo >> 1) + TK / 2 - 1) / (TK / 2);   // tiles hold <= TK/2 column pairs
+  s.ntj = (s.j_hi - s.j_lo + TJ - 1) / TJ;
   const int tiles = s.ntk * s.ntj;
   const int nown = s.i_end - s.i_begin;
   if (nown <= 0) { *n_partial_blocks = 0; return DPP_OK; }
@@ -943,11 +955,11 @@ int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const 
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
   const int pin = 1 + (int)(it & 1), pout = 1 + (int)((it + 1) & 1);
-  int nb = 0;
-  DPP_CHECK(launch_apply(ctx, F, nf, true, c, pin, F->buf[pout], slot, dtab, true, &nb));
-  if (!(ctx->world == 1 || comm_ipc_ready(ctx))) DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
   bool all_class_masked = true;
   for (int f = 0; f < nf; ++f) all_class_masked = all_class_masked && F->bc_full_gen[fld[f]] == ctx->bc_gen[fld[f]] && F->bc_full[fld[f]];
+  int nb = 0;
+  DPP_CHECK(launch_apply(ctx, F, nf, true, c, pin, F->buf[pout], slot, dtab, true, &nb, all_class_masked));
+  if (!(ctx->world == 1 || comm_ipc_ready(ctx))) DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
   if (all_class_masked) return DPP_OK;   // constrained rows never leave zero: no row fix-up needed
   // row elimination: w = p on constrained rows (identity rows of A_bc)
   const PadGeom g = pad_geom(ctx, F, nf);
