@@ -488,6 +488,9 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
     a.partials[bb * 2] = t0;
     a.partials[bb * 2 + 1] = t1;
   }
+  // halo planes stored into peer memory: make them visible system-wide before this block reports in
+  // (the last block's own system fence then orders them before the mailbox flag by cumulativity)
+  if (!INIT && (a.halo.peer_r[0] != nullptr || a.halo.peer_r[1] != nullptr)) __threadfence_system();
   if (a.fold.enabled && last_block_arrives(a.fold.counter, gridDim.x * gridDim.y, &last_flag))
     finish_reduction(a.partials, (int)(gridDim.x * gridDim.y), 2, a.fold.S, a.fold.hist, a.fold.post, 0, a.fold.ipc, sm);
 }
