@@ -22,6 +22,8 @@ struct Krylov {
   double *pb = nullptr;          // point-block inverse: i00,i01,i11  [3n]
   bool pb_valid = false;
   std::vector<double*> V;        // GMRES basis
+  double* d_gm = nullptr;        // device-resident GMRES state (gmres_run_device)
+  double* h_gm = nullptr;        // pinned mirror of its scalar head
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t inner_its = 0;
   int64_t apply_count = 0;
@@ -457,6 +459,208 @@ int gmres_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Device-resident KSPGMRES(m): the Hessenberg / Givens recurrence, PETSc's convergence test and the
+// history live in a device state block updated by single-thread kernels after each reduction; the host
+// launches a whole restart cycle (kernels past convergence are no-ops) and synchronises once per cycle
+// instead of once per iteration.  Same arithmetic, in the same order, as gmres_run below (the host-driven
+// version, kept for preconditioners that synchronise themselves: fieldsplit with inner Krylov solves).
+// ------------------------------------------------------------------------------------------------
+enum { G_IT = 0, G_ITS, G_RES, G_REASON, G_RNORM0, G_TTOL, G_RTOL, G_ATOL, G_DTOL, G_MAXIT, G_INV, G_HAPEND, G_HISTCAP,
+       G_M, G_NV, G_CC = 16, G_SS = 48, G_GRS = 80, G_Y = 114, G_H = 160, G_SIZE = 160 + 32 * 31 };
+
+__device__ __forceinline__ int gmres_test(double* G, int its, double rnorm) {  // KSPConvergedDefault
+  if (its == 0) {
+    G[G_RNORM0] = rnorm;
+    const double t = G[G_RTOL] * rnorm;
+    G[G_TTOL] = t > G[G_ATOL] ? t : G[G_ATOL];
+  }
+  if (!(rnorm == rnorm) || isinf(rnorm)) return DPP_DIVERGED_NANORINF;
+  if (rnorm <= G[G_TTOL]) return rnorm < G[G_ATOL] ? DPP_CONVERGED_ATOL : DPP_CONVERGED_RTOL;
+  if (rnorm >= G[G_DTOL] * G[G_RNORM0]) return DPP_DIVERGED_DTOL;
+  return 0;
+}
+
+// start of a restart cycle: S[S_TMP] = ||V0||^2 of the (preconditioned) residual
+__global__ void k_gmres_cycle_start(double* G, const double* S, double* hist) {
+  if (G[G_REASON] != 0.0) return;
+  const int its = (int)G[G_ITS], m = (int)G[G_M];
+  const double res = sqrt(S[S_TMP]);
+  if (hist != nullptr && its < (int)G[G_HISTCAP]) hist[its] = res;
+  int reason = 0;
+  if (res == 0.0) reason = DPP_CONVERGED_ATOL;
+  else {
+    reason = gmres_test(G, its, res);
+    if (!reason && its >= (int)G[G_MAXIT]) reason = DPP_DIVERGED_ITS;
+  }
+  G[G_RES] = res;
+  G[G_REASON] = (double)reason;
+  G[G_INV] = res != 0.0 ? 1.0 / res : 0.0;
+  G[G_HAPEND] = 0.0;
+  G[G_IT] = 0.0;
+  G[G_GRS] = res;
+  for (int q = 0; q < (m + 2) * (m + 1); ++q) G[G_H + q] = 0.0;
+}
+
+// after the Gram-Schmidt step of cycle iteration `it`: h = S[S_TMP .. S_TMP+it], ||w||^2 = S[S_TMP+36]
+__global__ void k_gmres_post(double* G, const double* S, double* hist) {
+  if (G[G_REASON] != 0.0) return;
+  const int it = (int)G[G_IT], m = (int)G[G_M];
+  const int ld = m + 1;
+  double* H = G + G_H;
+  double* cc = G + G_CC;
+  double* ss = G + G_SS;
+  double* grs = G + G_GRS;
+  const double tt = sqrt(S[S_TMP + kGmresNormOffset]);
+  bool hapend = false;
+  const double hapbnd = fmin(fabs(tt / grs[it]), 1e-30);
+  if (tt < hapbnd) hapend = true;
+  else G[G_INV] = 1.0 / tt;
+  G[G_HAPEND] = hapend ? 1.0 : 0.0;
+  for (int j = 0; j <= it; ++j) H[j * ld + it] = S[S_TMP + j];
+  H[(it + 1) * ld + it] = tt;
+  for (int j = 0; j < it; ++j) {
+    const double t = H[j * ld + it];
+    H[j * ld + it] = cc[j] * t + ss[j] * H[(j + 1) * ld + it];
+    H[(j + 1) * ld + it] = cc[j] * H[(j + 1) * ld + it] - ss[j] * t;
+  }
+  double res;
+  if (!hapend) {
+    const double a = H[it * ld + it], b = H[(it + 1) * ld + it];
+    const double t = sqrt(a * a + b * b);
+    if (t == 0.0) {
+      G[G_REASON] = (double)DPP_DIVERGED_BREAKDOWN;
+      return;
+    }
+    cc[it] = a / t;
+    ss[it] = b / t;
+    grs[it + 1] = -ss[it] * grs[it];
+    grs[it] = cc[it] * grs[it];
+    H[it * ld + it] = cc[it] * a + ss[it] * b;
+    res = fabs(grs[it + 1]);
+  } else {
+    res = 0.0;
+  }
+  const int its = (int)G[G_ITS] + 1;
+  int reason = gmres_test(G, its, res);
+  if (hapend && !reason) reason = DPP_DIVERGED_BREAKDOWN;
+  if (!reason && its >= (int)G[G_MAXIT]) reason = DPP_DIVERGED_ITS;  // the cycle stops here (ksp_max_it)
+  G[G_IT] = (double)(it + 1);
+  G[G_ITS] = (double)its;
+  G[G_RES] = res;
+  G[G_REASON] = (double)reason;
+  if (hist != nullptr && its < (int)G[G_HISTCAP]) hist[its] = res;
+}
+
+// end of a cycle: y = H^-1 g for the `it` completed iterations (runs whatever the reason)
+__global__ void k_gmres_solve_y(double* G) {
+  const int it = (int)G[G_IT], m = (int)G[G_M];
+  const int ld = m + 1;
+  const double* H = G + G_H;
+  const double* grs = G + G_GRS;
+  double* y = G + G_Y;
+  for (int k = it - 1; k >= 0; --k) {
+    double s = grs[k];
+    for (int j = k + 1; j < it; ++j) s -= H[k * ld + j] * y[j];
+    y[k] = s / H[k * ld + k];
+  }
+  G[G_NV] = (double)it;
+}
+
+int gmres_run_device(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* x, const Tol& tol, int restart,
+                     int hist_cap, KspOut* out) {
+  Krylov* K = ctx->krylov;
+  const VecLayout L = layout(ctx, 2);
+  const int64_t len = 2 * ctx->n_nodes;
+  const int slot = 0;
+  restart = std::max(1, std::min(restart, 30));
+  while ((int)K->V.size() < restart + 1) {
+    double* v = nullptr;
+    DPP_CHECK(dev_alloc(ctx, &v, len));
+    DPP_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * len, ctx->stream));
+    K->V.push_back(v);
+  }
+  if (!K->d_gm) {
+    DPP_CHECK(dev_alloc(ctx, &K->d_gm, G_SIZE));
+    DPP_CUDA(cudaMallocHost((void**)&K->h_gm, sizeof(double) * 16));
+  }
+  if (hist_cap > ctx->hist_cap[slot]) {
+    if (ctx->d_hist[slot]) cudaFree(ctx->d_hist[slot]);
+    ctx->d_hist[slot] = nullptr;
+    DPP_CHECK(dev_alloc(ctx, &ctx->d_hist[slot], hist_cap));
+    ctx->hist_cap[slot] = hist_cap;
+  }
+  double* hist = hist_cap > 0 ? ctx->d_hist[slot] : nullptr;
+  double* G = K->d_gm;
+  const double* S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
+  std::vector<double> g0(G_SIZE, 0.0);
+  g0[G_RTOL] = tol.rtol; g0[G_ATOL] = tol.atol; g0[G_DTOL] = tol.dtol; g0[G_MAXIT] = (double)tol.max_it;
+  g0[G_HISTCAP] = (double)std::min(hist_cap, ctx->hist_cap[slot]); g0[G_M] = (double)restart;
+  DPP_CUDA(cudaMemcpyAsync(G, g0.data(), sizeof(double) * G_SIZE, cudaMemcpyHostToDevice, ctx->stream));
+  DPP_CUDA(cudaStreamSynchronize(ctx->stream));  // g0 is a stack-lifetime host buffer
+  DPP_CHECK(vec_zero(ctx, x, len));
+  const bool pc_none = pc.type == DPP_PC_NONE;
+  const double* skip = G + G_REASON;
+  bool first = true;
+  int its = 0, reason = 0;
+  double res = 0.0;
+  while (true) {
+    // V0 = M^-1 (b - A x)
+    if (first) {
+      if (pc_none) DPP_CHECK(vec_copy(ctx, K->V[0], b, len));
+      else DPP_CHECK(pc_apply(ctx, pc, b, K->V[0]));
+    } else {
+      DPP_CHECK(halo(ctx, x, 2));
+      int nb = 0;
+      DPP_CHECK(apply_spec(ctx, op, x, K->w, false, nullptr, &nb));
+      DPP_CHECK(vec_axpby(ctx, L, 1.0, b, -1.0, K->w));  // w = b - A x
+      if (pc_none) DPP_CHECK(vec_copy(ctx, K->V[0], K->w, len));
+      else DPP_CHECK(pc_apply(ctx, pc, K->w, K->V[0]));
+    }
+    first = false;
+    DPP_CHECK(vec_dot2(ctx, L, K->V[0], K->V[0], nullptr, nullptr, slot, POST_NONE));
+    k_gmres_cycle_start<<<1, 1, 0, ctx->stream>>>(G, S, hist);
+    ctx->launches++;
+    DPP_CHECK(vec_scale_dev(ctx, L, K->V[0], G + G_INV, skip, nullptr));
+    for (int it = 0; it < restart; ++it) {
+      double* vnew = K->V[it + 1];
+      DPP_CHECK(halo(ctx, K->V[it], 2));
+      int nb = 0;
+      if (pc_none) {
+        DPP_CHECK(apply_spec(ctx, op, K->V[it], vnew, false, skip, &nb));
+      } else {
+        DPP_CHECK(apply_spec(ctx, op, K->V[it], K->w, false, skip, &nb));
+        DPP_CHECK(pc_apply(ctx, pc, K->w, vnew));  // pointwise preconditioners only: harmless past convergence
+      }
+      DPP_CHECK(gmres_mdot(ctx, L, K->V.data(), it + 1, vnew, slot, skip));
+      DPP_CHECK(gmres_maxpy_norm(ctx, L, K->V.data(), it + 1, vnew, slot, skip));
+      k_gmres_post<<<1, 1, 0, ctx->stream>>>(G, S, hist);
+      ctx->launches++;
+      DPP_CHECK(vec_scale_dev(ctx, L, vnew, G + G_INV, skip, G + G_HAPEND));
+    }
+    k_gmres_solve_y<<<1, 1, 0, ctx->stream>>>(G);
+    ctx->launches++;
+    DPP_CHECK(vec_maxpy_dev(ctx, L, K->V.data(), restart, G + G_Y, G + G_NV, x));
+    DPP_CUDA(cudaMemcpyAsync(K->h_gm, G, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+    its = (int)K->h_gm[G_ITS];
+    reason = (int)K->h_gm[G_REASON];
+    res = K->h_gm[G_RES];
+    if (reason) break;
+    if (its >= tol.max_it) { reason = DPP_DIVERGED_ITS; break; }
+  }
+  out->its = its;
+  out->reason = reason;
+  out->rnorm = res;
+  const int nh = std::min(its + 1, std::min(hist_cap, ctx->hist_cap[slot]));
+  out->hist.resize(std::max(nh, 0));
+  if (nh > 0) {
+    DPP_CUDA(cudaMemcpyAsync(out->hist.data(), ctx->d_hist[slot], sizeof(double) * nh, cudaMemcpyDeviceToHost, ctx->stream));
+    DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return DPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Block Picard (scale splitting), SURVEY A.6
 // ------------------------------------------------------------------------------------------------
 int picard_run(dpp_context* ctx, const dpp_options* opt, const double* b, double* d, const Tol& tol, double bnorm,
@@ -647,7 +851,12 @@ int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_r
       break;
     }
     case DPP_KSP_GMRES:
-      rc = gmres_run(ctx, mono, pc, K->b, K->x, tol, opt->gmres_restart, &out);
+      // pointwise preconditioners: whole restart cycles run from device state; fieldsplit (inner Krylov
+      // solves that synchronise with the host anyway) keeps the host-driven recurrence
+      if (opt->pc_type != DPP_PC_FIELDSPLIT && getenv("DPP_GMRES_HOST") == nullptr)
+        rc = gmres_run_device(ctx, mono, pc, K->b, K->x, tol, opt->gmres_restart, std::max(hist_cap, 0), &out);
+      else
+        rc = gmres_run(ctx, mono, pc, K->b, K->x, tol, opt->gmres_restart, &out);
       break;
     case DPP_KSP_PICARD:
       rc = picard_run(ctx, opt, K->b, K->x, tol, bnorm, &out);
@@ -706,6 +915,8 @@ void krylov_destroy(dpp_context* ctx) {
   for (double* v : vs)
     if (v) cudaFree(v);
   for (double* v : K->V) cudaFree(v);
+  if (K->d_gm) cudaFree(K->d_gm);
+  if (K->h_gm) cudaFreeHost(K->h_gm);
   for (auto& e : K->ev)
     if (e) cudaEventDestroy(e);
   delete K;

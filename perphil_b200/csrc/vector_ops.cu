@@ -179,8 +179,9 @@ struct VecPtrs {
 
 // partials[b*width + j] = <V_j, w> over the block's chunk, j < nv (classical Gram-Schmidt VecMDot)
 __global__ void __launch_bounds__(VT) k_mdot(VecLayout L, VecPtrs V, int nv, const double* __restrict__ w,
-                                              double* __restrict__ partials, int width) {
+                                              double* __restrict__ partials, int width, const double* skip) {
   __shared__ double sm[VT / 32];
+  if (skip != nullptr && *skip != 0.0) return;
   const Chunk c = my_chunk(L);
   const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
   for (int j0 = 0; j0 < nv; j0 += 8) {
@@ -204,11 +205,15 @@ __global__ void __launch_bounds__(VT) k_mdot(VecLayout L, VecPtrs V, int nv, con
 }
 
 // w -= sum_j h[j] V_j ; partial ||w||^2      (h = S[S_TMP .. S_TMP+nv))
+// nv_dev (optional): the number of vectors is read from device memory (GMRES cycle length)
 __global__ void __launch_bounds__(VT) k_maxpy_norm(VecLayout L, VecPtrs V, int nv, double* __restrict__ w,
                                                     const double* __restrict__ h, double sign,
-                                                    double* __restrict__ partials) {
+                                                    double* __restrict__ partials, const double* skip,
+                                                    const double* nv_dev) {
   __shared__ double sm[VT / 32];
   __shared__ double hs[32];
+  if (skip != nullptr && *skip != 0.0) return;
+  if (nv_dev != nullptr) nv = (int)*nv_dev;
   if (threadIdx.x < nv) hs[threadIdx.x] = h[threadIdx.x];
   __syncthreads();
   const Chunk c = my_chunk(L);
@@ -329,17 +334,19 @@ int cg_xr_update(dpp_context* ctx, const VecLayout& L, double* x, double* r, con
   return DPP_OK;
 }
 
-int gmres_mdot(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, const double* w, int slot) {
+int gmres_mdot(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, const double* w, int slot,
+               const double* skip) {
   VecPtrs P{};
   for (int j = 0; j < nv; ++j) P.v[j] = V[j];
   dim3 grid(vec_launch_blocks(ctx, L), L.nf);
-  k_mdot<<<grid, VT, 0, ctx->stream>>>(L, P, nv, w, ctx->d_partials, nv);
+  k_mdot<<<grid, VT, 0, ctx->stream>>>(L, P, nv, w, ctx->d_partials, nv, skip);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   return reduce_partials(ctx, grid.x * grid.y, nv, slot, POST_NONE);
 }
 
-int gmres_maxpy_norm(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, double* w, int slot) {
+int gmres_maxpy_norm(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, double* w, int slot,
+                     const double* skip) {
   VecPtrs P{};
   for (int j = 0; j < nv; ++j) P.v[j] = V[j];
   const double* S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
@@ -347,7 +354,7 @@ int gmres_maxpy_norm(dpp_context* ctx, const VecLayout& L, const double* const* 
   double* hcopy = ctx->d_scalars + (size_t)kNumScalars - 40;
   DPP_CUDA(cudaMemcpyAsync(hcopy, S + S_TMP, sizeof(double) * nv, cudaMemcpyDeviceToDevice, ctx->stream));
   dim3 grid(vec_launch_blocks(ctx, L), L.nf);
-  k_maxpy_norm<<<grid, VT, 0, ctx->stream>>>(L, P, nv, w, hcopy, -1.0, ctx->d_partials);
+  k_maxpy_norm<<<grid, VT, 0, ctx->stream>>>(L, P, nv, w, hcopy, -1.0, ctx->d_partials, skip, nullptr);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   // h stays in S[S_TMP .. S_TMP+nv) for the host; ||w||^2 goes to S[S_TMP + kGmresNormOffset]
@@ -361,9 +368,36 @@ int vec_maxpy_host(dpp_context* ctx, const VecLayout& L, const double* const* V,
   double* hcopy = ctx->d_scalars + (size_t)kNumScalars - 40;
   DPP_CUDA(cudaMemcpyAsync(hcopy, coef, sizeof(double) * nv, cudaMemcpyHostToDevice, ctx->stream));
   dim3 grid(vec_launch_blocks(ctx, L), L.nf);
-  k_maxpy_norm<<<grid, VT, 0, ctx->stream>>>(L, P, nv, x, hcopy, 1.0, nullptr);
+  k_maxpy_norm<<<grid, VT, 0, ctx->stream>>>(L, P, nv, x, hcopy, 1.0, nullptr, nullptr, nullptr);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+
+// x += sum_{j < *nv_dev} coef_dev[j] V_j   (coefficients and count live on the device)
+int vec_maxpy_dev(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv_max, const double* coef_dev,
+                  const double* nv_dev, double* x) {
+  VecPtrs P{};
+  for (int j = 0; j < nv_max; ++j) P.v[j] = V[j];
+  dim3 grid(vec_launch_blocks(ctx, L), L.nf);
+  k_maxpy_norm<<<grid, VT, 0, ctx->stream>>>(L, P, nv_max, x, coef_dev, 1.0, nullptr, nullptr, nv_dev);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  return DPP_OK;
+}
+
+__global__ void __launch_bounds__(VT) k_scale_dev(VecLayout L, double* __restrict__ v, const double* __restrict__ factor,
+                                                   const double* skip0, const double* skip1) {
+  if ((skip0 != nullptr && *skip0 != 0.0) || (skip1 != nullptr && *skip1 != 0.0)) return;
+  const double a = *factor;
+  const Chunk c = my_chunk(L);
+  for (long long i = c.begin + threadIdx.x; i < c.end; i += VT) v[i] *= a;
+}
+
+// v *= *factor_dev unless *skip0 or *skip1 is non-zero
+int vec_scale_dev(dpp_context* ctx, const VecLayout& L, double* v, const double* factor_dev, const double* skip0,
+                  const double* skip1) {
+  VLAUNCH(k_scale_dev, L, v, factor_dev, skip0, skip1);
   return DPP_OK;
 }
 

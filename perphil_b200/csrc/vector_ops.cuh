@@ -61,8 +61,14 @@ int cg_fused_plain_apply(dpp_context* ctx, int nf, const Coef& c, bool want_dot,
 int cg_fused_pad_from(dpp_context* ctx, int which /*0 r, 1 p0, 2 p1, 3 w, 4 x*/, const double* src);
 
 // GMRES kernels
-int gmres_mdot(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, const double* w, int slot);
-int gmres_maxpy_norm(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, double* w, int slot);
+int gmres_mdot(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, const double* w, int slot,
+               const double* skip = nullptr);
+int gmres_maxpy_norm(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, double* w, int slot,
+                     const double* skip = nullptr);
+int vec_maxpy_dev(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv_max, const double* coef_dev,
+                  const double* nv_dev, double* x);
+int vec_scale_dev(dpp_context* ctx, const VecLayout& L, double* v, const double* factor_dev, const double* skip0,
+                  const double* skip1);
 // x += sum_j coef[j] V_j  (coef: host array, nv <= 32)
 int vec_maxpy_host(dpp_context* ctx, const VecLayout& L, const double* const* V, int nv, const double* coef,
                    double* x);
