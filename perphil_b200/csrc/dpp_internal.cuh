@@ -145,7 +145,8 @@ struct dpp_context {
   int hist_cap[2] = {0, 0};
 
   void set_error(const std::string& s) { err = s; }
-  void invalidate() { diag_valid = false; }
+  unsigned long long state_gen = 0;  // bumped whenever parameters / BCs / numbering / partition change
+  void invalidate() { diag_valid = false; ++state_gen; }
 };
 
 namespace dpp {

@@ -12,8 +12,19 @@
 
 namespace dpp {
 
+// A captured CUDA graph of one launch-bound inner loop (a batch of CG iterations, a GMRES restart cycle):
+// every kernel argument of such a loop is the same from one batch / cycle to the next (scalars live in
+// device memory), so it is captured once and replayed; `key` ties it to the solver configuration.
+struct GraphSlot {
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long key = 0;
+  long long nodes = 0;
+  bool broken = false;  // capture failed once on this handle: keep launching directly
+};
+
 struct Krylov {
   int64_t nvec = 0;  // 2 * n_nodes
+  GraphSlot cg_graph[2], gmres_graph;
   double *b = nullptr, *x = nullptr, *r = nullptr, *p = nullptr, *w = nullptr, *z = nullptr, *t = nullptr;
   double *u0 = nullptr;
   // single-field work vectors for block solves
@@ -73,6 +84,55 @@ __global__ void k_sub(long long n, const double* __restrict__ a, const double* _
 
 int ew_blocks(const dpp_context* ctx, long long n) {
   return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16));
+}
+
+unsigned long long mix(unsigned long long h, unsigned long long v) {
+  h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+  return h;
+}
+
+// run `body` (which only enqueues work on ctx->stream) through a cached CUDA graph
+template <class F>
+int run_graphed(dpp_context* ctx, GraphSlot& gs, unsigned long long key, F&& body) {
+  if (gs.broken || ctx->world > 1 || getenv("DPP_NO_GRAPH") != nullptr) return body();
+  if (gs.exec != nullptr && gs.key == key) {
+    DPP_CUDA(cudaGraphLaunch(gs.exec, ctx->stream));
+    ctx->launches += gs.nodes;
+    return DPP_OK;
+  }
+  if (gs.exec != nullptr) {
+    cudaGraphExecDestroy(gs.exec);
+    gs.exec = nullptr;
+  }
+  const long long l0 = ctx->launches;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    gs.broken = true;
+    return body();
+  }
+  const int rc = body();
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+  if (rc != DPP_OK || e != cudaSuccess || g == nullptr) {
+    cudaGetLastError();
+    if (g) cudaGraphDestroy(g);
+    gs.broken = true;
+    ctx->launches = l0;
+    return body();  // nothing was executed during the failed capture
+  }
+  gs.nodes = ctx->launches - l0;
+  const cudaError_t ei = cudaGraphInstantiate(&gs.exec, g, 0);
+  cudaGraphDestroy(g);
+  if (ei != cudaSuccess) {
+    cudaGetLastError();
+    gs.exec = nullptr;
+    gs.broken = true;
+    ctx->launches = l0;
+    return body();
+  }
+  gs.key = key;
+  DPP_CUDA(cudaGraphLaunch(gs.exec, ctx->stream));
+  return DPP_OK;
 }
 
 VecLayout layout(const dpp_context* ctx, int nf) {
@@ -172,13 +232,23 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
     DPP_CHECK(scalars_fetch(ctx, slot));
     const int every = std::max(1, check_every);
     long long kk = 0;
-    while (h[S_REASON] == 0.0) {
-      for (int k = 0; k < every; ++k, ++kk) {
-        DPP_CHECK(cg_fused_apply(ctx, op.nf, coef, kk, fld, slot, dtab));
-        ctx->krylov->apply_count++;
+    auto batch = [&](long long kk0) -> int {
+      for (int k = 0; k < every; ++k) {
+        DPP_CHECK(cg_fused_apply(ctx, op.nf, coef, kk0 + k, fld, slot, dtab));
         DPP_CHECK(cg_fused_r_update(ctx, op.nf, fld, slot, dtab));
         DPP_CHECK(cg_fused_halo_r(ctx, op.nf, true, slot));
       }
+      return DPP_OK;
+    };
+    // the p ping-pong repeats with period 2: batches of an even number of iterations are identical launch
+    // sequences -> replayed as one CUDA graph after the first (directly launched) batch
+    unsigned long long key = mix(mix(mix(ctx->state_gen, (unsigned long long)op.nf * 16 + op.row * 4 + pc.type),
+                                     (unsigned long long)every), (unsigned long long)(uintptr_t)hist_device(ctx, slot));
+    while (h[S_REASON] == 0.0) {
+      if (kk == 0 || (every & 1)) DPP_CHECK(batch(kk));
+      else DPP_CHECK(run_graphed(ctx, ctx->krylov->cg_graph[slot], key, [&]() { return batch(kk); }));
+      kk += every;
+      ctx->krylov->apply_count += every;
       DPP_CHECK(scalars_fetch(ctx, slot));
     }
     DPP_CHECK(cg_fused_x_finalize(ctx, op.nf, (long long)h[S_ITS], slot, x));
@@ -601,7 +671,7 @@ int gmres_run_device(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b
   const bool pc_none = pc.type == DPP_PC_NONE;
   const double* skip = G + G_REASON;
   bool first = true;
-  int its = 0, reason = 0;
+  int its = 0, reason = 0, n_cycles = 0;
   double res = 0.0;
   while (true) {
     // V0 = M^-1 (b - A x)
@@ -620,26 +690,35 @@ int gmres_run_device(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b
     DPP_CHECK(vec_dot2(ctx, L, K->V[0], K->V[0], nullptr, nullptr, slot, POST_NONE));
     k_gmres_cycle_start<<<1, 1, 0, ctx->stream>>>(G, S, hist);
     ctx->launches++;
-    DPP_CHECK(vec_scale_dev(ctx, L, K->V[0], G + G_INV, skip, nullptr));
-    for (int it = 0; it < restart; ++it) {
-      double* vnew = K->V[it + 1];
-      DPP_CHECK(halo(ctx, K->V[it], 2));
-      int nb = 0;
-      if (pc_none) {
-        DPP_CHECK(apply_spec(ctx, op, K->V[it], vnew, false, skip, &nb));
-      } else {
-        DPP_CHECK(apply_spec(ctx, op, K->V[it], K->w, false, skip, &nb));
-        DPP_CHECK(pc_apply(ctx, pc, K->w, vnew));  // pointwise preconditioners only: harmless past convergence
+    auto cycle = [&]() -> int {
+      DPP_CHECK(vec_scale_dev(ctx, L, K->V[0], G + G_INV, skip, nullptr));
+      for (int it = 0; it < restart; ++it) {
+        double* vnew = K->V[it + 1];
+        DPP_CHECK(halo(ctx, K->V[it], 2));
+        int nb = 0;
+        if (pc_none) {
+          DPP_CHECK(apply_spec(ctx, op, K->V[it], vnew, false, skip, &nb));
+        } else {
+          DPP_CHECK(apply_spec(ctx, op, K->V[it], K->w, false, skip, &nb));
+          DPP_CHECK(pc_apply(ctx, pc, K->w, vnew));  // pointwise preconditioners only: harmless past convergence
+        }
+        DPP_CHECK(gmres_mdot(ctx, L, K->V.data(), it + 1, vnew, slot, skip));
+        DPP_CHECK(gmres_maxpy_norm(ctx, L, K->V.data(), it + 1, vnew, slot, skip));
+        k_gmres_post<<<1, 1, 0, ctx->stream>>>(G, S, hist);
+        ctx->launches++;
+        DPP_CHECK(vec_scale_dev(ctx, L, vnew, G + G_INV, skip, G + G_HAPEND));
       }
-      DPP_CHECK(gmres_mdot(ctx, L, K->V.data(), it + 1, vnew, slot, skip));
-      DPP_CHECK(gmres_maxpy_norm(ctx, L, K->V.data(), it + 1, vnew, slot, skip));
-      k_gmres_post<<<1, 1, 0, ctx->stream>>>(G, S, hist);
+      k_gmres_solve_y<<<1, 1, 0, ctx->stream>>>(G);
       ctx->launches++;
-      DPP_CHECK(vec_scale_dev(ctx, L, vnew, G + G_INV, skip, G + G_HAPEND));
-    }
-    k_gmres_solve_y<<<1, 1, 0, ctx->stream>>>(G);
-    ctx->launches++;
-    DPP_CHECK(vec_maxpy_dev(ctx, L, K->V.data(), restart, G + G_Y, G + G_NV, x));
+      DPP_CHECK(vec_maxpy_dev(ctx, L, K->V.data(), restart, G + G_Y, G + G_NV, x));
+      return DPP_OK;
+    };
+    // every restart cycle is the same launch sequence (state and scalars live on the device): one CUDA graph
+    const unsigned long long key = mix(mix(mix(ctx->state_gen, (unsigned long long)restart * 64 + pc.type * 4 + op.mode),
+                                           (unsigned long long)(uintptr_t)hist), (unsigned long long)(uintptr_t)x);
+    if (n_cycles == 0) DPP_CHECK(cycle());   // first cycle directly: lazy allocations / attributes happen here
+    else DPP_CHECK(run_graphed(ctx, K->gmres_graph, key, cycle));
+    ++n_cycles;
     DPP_CUDA(cudaMemcpyAsync(K->h_gm, G, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
     DPP_CUDA(cudaStreamSynchronize(ctx->stream));
     its = (int)K->h_gm[G_ITS];
@@ -915,6 +994,8 @@ void krylov_destroy(dpp_context* ctx) {
   for (double* v : vs)
     if (v) cudaFree(v);
   for (double* v : K->V) cudaFree(v);
+  for (GraphSlot* gsl : {&K->cg_graph[0], &K->cg_graph[1], &K->gmres_graph})
+    if (gsl->exec) cudaGraphExecDestroy(gsl->exec);
   if (K->d_gm) cudaFree(K->d_gm);
   if (K->h_gm) cudaFreeHost(K->h_gm);
   for (auto& e : K->ev)
