@@ -13,12 +13,16 @@ if world > 1:
     comm = SlabComm.from_env()
     torch.cuda.set_device(comm.device)
 rank = comm.rank if comm else 0
-want = [int(a) for a in sys.argv[1:]] or [1, 2, 4, 5]
+want = [a if a == "4w" else int(a) for a in sys.argv[1:]] or [1, 2, 4, 5]
 out = []
 
 
-def problem(cells, degree, k2, beta, bc):
-    mesh = pb.UnitSquareMesh(*cells, comm=comm) if len(cells) == 2 else pb.UnitCubeMesh(*cells, comm=comm)
+def problem(cells, degree, k2, beta, bc, lengths=None):
+    if lengths is not None:
+        from perphil_b200.mesh import Mesh
+        mesh = Mesh(cells, lengths=lengths, comm=comm)
+    else:
+        mesh = pb.UnitSquareMesh(*cells, comm=comm) if len(cells) == 2 else pb.UnitCubeMesh(*cells, comm=comm)
     _, V = pb.create_function_spaces(mesh, pressure_deg=degree)
     W = V * V
     prm = pb.DPPParameters(k1=1.0, k2=k2, beta=beta, mu=1.0)
@@ -30,8 +34,8 @@ def problem(cells, degree, k2, beta, bc):
     return W, V, prm, [pb.DirichletBC(W.sub(0), g1, "on_boundary"), pb.DirichletBC(W.sub(1), g2, "on_boundary")]
 
 
-def run(tag, cells, degree, preset_name, k2=1e-2, beta=1.0, bc="manufactured", nonlinear=False, repeats=2):
-    W, V, prm, bcs = problem(cells, degree, k2, beta, bc)
+def run(tag, cells, degree, preset_name, k2=1e-2, beta=1.0, bc="manufactured", nonlinear=False, repeats=2, lengths=None):
+    W, V, prm, bcs = problem(cells, degree, k2, beta, bc, lengths)
     fn = pb.solve_dpp_nonlinear if nonlinear else pb.solve_dpp
     preset = getattr(pb, preset_name)
     best = None
@@ -69,6 +73,14 @@ if 4 in want:
     run(f"4: 3D hex Q2 {N4}^3, block Picard (scale splitting), Jacobi-CG blocks", (N4,) * 3, 2, "B200_PICARD_SPLIT_PARAMS",
         nonlinear=True, repeats=2 if world > 1 else 1)
     run(f"4: 3D hex Q2 {N4}^3, Jacobi-CG monolithic", (N4,) * 3, 2, "B200_CG_JACOBI_PARAMS", repeats=2 if world > 1 else 1)
+if "4w" in want:
+    # weak scaling of config 4: a fixed 24 x 192 x 192-cell Q2 slab per GPU (192^3 at 8 GPUs), cubic cells kept by
+    # growing the domain length along x with the rank count
+    cw = (24 * world, 192, 192)
+    run(f"4 weak: 3D hex Q2 {cw[0]}x192x192 (24 cell layers per GPU), block Picard, Jacobi-CG blocks", cw, 2,
+        "B200_PICARD_SPLIT_PARAMS", nonlinear=True, repeats=2, lengths=(world / 8.0, 1.0, 1.0))
+    run(f"4 weak: 3D hex Q2 {cw[0]}x192x192 (24 cell layers per GPU), Jacobi-CG monolithic", cw, 2,
+        "B200_CG_JACOBI_PARAMS", repeats=2, lengths=(world / 8.0, 1.0, 1.0))
 if 5 in want:
     run(f"5: 3D hex Q1 {N5}^3 k2=1e-6 beta=1e2, GMRES + multiplicative fieldsplit", (N5,) * 3, 1,
         "B200_GMRES_FIELDSPLIT_PARAMS", k2=1e-6, beta=1e2, bc="const")
