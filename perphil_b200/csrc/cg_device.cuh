@@ -10,7 +10,7 @@ namespace dpp {
 namespace {
 
 constexpr int VT = 256;   // threads per block of every kernel that reduces
-constexpr int kFinishSmem = VT / 32 + kMboxEntry + 2;
+constexpr int kFinishSmem = VT / 32 + kMboxEntry + 2 + kMaxIpcRanks * (kMboxEntry - 1);
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -83,17 +83,27 @@ __device__ __forceinline__ void apply_post(double* S, double* hist, int post) {
 
 // Reduction epilogue run by ONE block of VT threads: S[S_TMP + out_offset + w] = sum over blocks (fixed
 // order) of partials[b*width + w], all-reduced over the ranks' mailboxes when ipc.world > 1, then the
-// post-op.  Mailbox protocol: every rank writes its sums into slot (seq & 1) of EVERY rank's mailbox,
-// flag last (after a system fence, which also orders the halo stores of the producing kernel before the
-// flag); then waits until all ranks' entries of this sequence number arrived in its own mailbox and adds
-// them in rank order -- the same order everywhere, so all ranks hold bit-identical sums.  Two slots are
-// enough: a rank can run at most one reduction ahead of the slowest one.
-// sm: kFinishSmem = VT/32 + kMboxEntry + 2 doubles of shared memory.
+// post-op.  Mailbox protocol: every rank writes its sums into slot (seq & 1) of EVERY rank's mailbox, then
+// waits until all ranks' entries of this sequence number arrived in its own mailbox and adds them in rank
+// order -- the same order everywhere, so all ranks hold bit-identical sums.  Two slots are enough: a rank
+// can run at most one reduction ahead of the slowest one.
+//   ipc.ll = 1 (default): every 8-byte word carries 32 bits of payload and the 32-bit sequence tag, so a
+//     value IS its own flag (two words per double) and no fence separates data from flag: one NVLink
+//     traversal per reduction.  `sys_release`: the producing kernel stored into peer memory (halo push);
+//     the sending threads then execute ONE fence.acq_rel.sys before the words -- cumulative over the
+//     stores of all blocks, which reported in through gpu-scope fence + arrival counter -- and the
+//     receivers poll with ld.acquire.sys (LDG.STRONG.SYS + CCTL.IVALL, no MEMBAR).  A MEMBAR.SYS costs
+//     ~1.2 us even with nothing outstanding (measured, profiles/r01_exchange_cost.md), so reductions that
+//     order no remote data (<p,Ap>: only the write-after-read hazard on the ghost planes, whose loads have
+//     completed before the block reported in) skip it.
+//   ipc.ll = 0 (DPP_MBOX_LL=0): values, system fence, separate flag word (two traversals).
+// sm: kFinishSmem doubles of shared memory.
 __device__ __forceinline__ void finish_reduction(const double* __restrict__ partials, int nblocks, int width, double* S,
                                                  double* hist, int post, int out_offset, const IpcReduce& ipc,
-                                                 double* sm) {
+                                                 double* sm, bool sys_release = true) {
   double* vals = sm + VT / 32;
   volatile int* timed_out = reinterpret_cast<volatile int*>(sm + VT / 32 + kMboxEntry);
+  double* recv = sm + VT / 32 + kMboxEntry + 2;   // [world][kMboxEntry - 1]
   const int tid = threadIdx.x + threadIdx.y * blockDim.x;
   if (tid == 0) *timed_out = 0;
   for (int w = 0; w < width; ++w) {
@@ -109,20 +119,48 @@ __device__ __forceinline__ void finish_reduction(const double* __restrict__ part
   const unsigned long long seq = dist ? *seq_sm : 0ull;
   const int slot = (int)(seq & 1ull);
   if (dist && tid < ipc.world) {
-    const double tag = (double)seq;
-    double* dst = ipc.peer[tid] + ((size_t)slot * ipc.world + ipc.rank) * kMboxEntry;
-    for (int w = 0; w < width; ++w) dst[w] = vals[w];
-    __threadfence_system();
-    *reinterpret_cast<volatile double*>(dst + kMboxEntry - 1) = tag;
-    const volatile double* src = ipc.local + ((size_t)slot * ipc.world + tid) * kMboxEntry;
+    const size_t mine = ((size_t)slot * ipc.world + ipc.rank) * kMboxWords;
+    const size_t theirs = ((size_t)slot * ipc.world + tid) * kMboxWords;
     const long long t0 = clock64();
-    while (src[kMboxEntry - 1] != tag) {
-      if (clock64() - t0 > 60000000000LL) {  // ~30 s: a peer died; report instead of hanging the GPU
-        *timed_out = 1;
-        break;
+    if (ipc.ll) {
+      const unsigned long long tag = (seq & 0xffffffffull) << 32;
+      volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(ipc.peer[tid]) + mine;
+      if (sys_release && ipc.ll != 2) asm volatile("fence.acq_rel.sys;" ::: "memory");
+      for (int w = 0; w < width; ++w) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[w]);
+        dst[2 * w] = tag | (bits & 0xffffffffull);
+        dst[2 * w + 1] = tag | (bits >> 32);
       }
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(ipc.local) + theirs;
+      for (int w = 0; w < width; ++w) {
+        unsigned long long lo, hi;
+        while (true) {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(lo) : "l"(src + 2 * w) : "memory");
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(hi) : "l"(src + 2 * w + 1) : "memory");
+          if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+          if (clock64() - t0 > 60000000000LL) {  // ~30 s: a peer died; report instead of hanging the GPU
+            *timed_out = 1;
+            break;
+          }
+        }
+        recv[tid * (kMboxEntry - 1) + w] = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+      }
+    } else {
+      const double tag = (double)seq;
+      double* dst = ipc.peer[tid] + mine;
+      for (int w = 0; w < width; ++w) dst[w] = vals[w];
+      __threadfence_system();
+      *reinterpret_cast<volatile double*>(dst + kMboxEntry - 1) = tag;
+      const volatile double* src = ipc.local + theirs;
+      while (src[kMboxEntry - 1] != tag) {
+        if (clock64() - t0 > 60000000000LL) {
+          *timed_out = 1;
+          break;
+        }
+      }
+      for (int w = 0; w < width; ++w) recv[tid * (kMboxEntry - 1) + w] = src[w];
+      __threadfence_system();
     }
-    __threadfence_system();
   }
   __syncthreads();
   if (tid == 0) {
@@ -133,8 +171,7 @@ __device__ __forceinline__ void finish_reduction(const double* __restrict__ part
         double t = vals[w];
         if (dist) {
           t = 0.0;
-          for (int r = 0; r < ipc.world; ++r)
-            t += reinterpret_cast<const volatile double*>(ipc.local)[((size_t)slot * ipc.world + r) * kMboxEntry + w];
+          for (int r = 0; r < ipc.world; ++r) t += recv[r * (kMboxEntry - 1) + w];
         }
         S[S_TMP + out_offset + w] = t;
       }

@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
       s.dot_partials[blockIdx.x] = t;
     }
     if (FUSED && s.fold.enabled && last_block_arrives(s.fold.counter, gridDim.x, &sm.last_flag))
-      finish_reduction(s.dot_partials, (int)gridDim.x, 1, s.fold.S, s.fold.hist, s.fold.post, 0, s.fold.ipc, sm.fin);
+      finish_reduction(s.dot_partials, (int)gridDim.x, 1, s.fold.S, s.fold.hist, s.fold.post, 0, s.fold.ipc, sm.fin,
+                       s.fold.ipc.ll == 3);
   }
 }
 
@@ -488,11 +489,15 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
     a.partials[bb * 2] = t0;
     a.partials[bb * 2 + 1] = t1;
   }
-  // halo planes stored into peer memory: make them visible system-wide before this block reports in
-  // (the last block's own system fence then orders them before the mailbox flag by cumulativity)
-  if (!INIT && (a.halo.peer_r[0] != nullptr || a.halo.peer_r[1] != nullptr)) __threadfence_system();
+  // Halo planes stored into peer memory: every block reports in through a gpu-scope fence + the arrival
+  // counter (last_block_arrives); the last block's single system-scope fence before the mailbox words is
+  // cumulative over all of them (finish_reduction, sys_release).  A system fence in every pushing block
+  // cost 2 us per iteration: MEMBAR.SYS stalls the whole SM, and the pushing blocks sit on every SM.
+  const bool remote = !INIT && (a.halo.peer_r[0] != nullptr || a.halo.peer_r[1] != nullptr);
+  if (remote && a.halo.debug_fence_all) __threadfence_system();
   if (a.fold.enabled && last_block_arrives(a.fold.counter, gridDim.x * gridDim.y, &last_flag))
-    finish_reduction(a.partials, (int)(gridDim.x * gridDim.y), 2, a.fold.S, a.fold.hist, a.fold.post, 0, a.fold.ipc, sm);
+    finish_reduction(a.partials, (int)(gridDim.x * gridDim.y), 2, a.fold.S, a.fold.hist, a.fold.post, 0, a.fold.ipc, sm,
+                     remote || INIT);
 }
 
 // boundary planes of r -> the neighbours' ghost planes (start of a solve)

@@ -83,7 +83,7 @@ struct Comm {
   // peer-memory fast path
   bool ipc = false;                       // mailbox all-reduce active
   bool ipc_halo = false;                  // halo push into the neighbours' residual vectors active
-  double* mbox = nullptr;                 // own mailbox [2][world][kMboxEntry]
+  double* mbox = nullptr;                 // own mailbox [2][world][kMboxWords]
   double* mbox_peer[kMaxIpcRanks] = {};   // mapped mailboxes of the other ranks
   double* r_peer[2] = {nullptr, nullptr}; // mapped residual vectors of rank-1 / rank+1
   long long r_peer_field[2] = {0, 0}, r_peer_ghost_off[2] = {0, 0};
@@ -201,21 +201,25 @@ IpcReduce comm_ipc_reduce_args(dpp_context* ctx) {
   a.local = C->mbox;
   for (int r = 0; r < ctx->world; ++r) a.peer[r] = (r == ctx->rank) ? C->mbox : C->mbox_peer[r];
   a.rank = ctx->rank;
-  a.world = ctx->world;
+  a.world = getenv("DPP_DEBUG_NO_MBOX") ? 1 : ctx->world;   // timing experiments only: local sums
   // the sequence counter lives behind the mailbox entries; it advances only when an exchange really runs
-  a.seq_dev = reinterpret_cast<unsigned long long*>(C->mbox + 2 * kMaxIpcRanks * kMboxEntry);
+  a.seq_dev = reinterpret_cast<unsigned long long*>(C->mbox + 2 * kMaxIpcRanks * kMboxWords);
+  const char* ll = getenv("DPP_MBOX_LL");
+  a.ll = (ll != nullptr) ? atoi(ll) : 1;
   return a;
 }
 
 IpcHalo comm_ipc_halo(const dpp_context* ctx) {
   IpcHalo h{};
   const Comm* C = ctx->comm;
-  if (C && C->ipc && C->ipc_halo)
+  // DPP_DEBUG_NO_PUSH: timing experiments only (the solve is wrong without the ghost planes)
+  if (C && C->ipc && C->ipc_halo && getenv("DPP_DEBUG_NO_PUSH") == nullptr)
     for (int s = 0; s < 2; ++s) {
       h.peer_r[s] = C->r_peer[s];
       h.peer_field[s] = C->r_peer_field[s];
       h.peer_ghost_off[s] = C->r_peer_ghost_off[s];
     }
+  h.debug_fence_all = getenv("DPP_DEBUG_FENCE_ALL") != nullptr;
   return h;
 }
 
@@ -289,8 +293,8 @@ int dpp_comm_ipc_export(dpp_handle ctx, void* blob_out) {
   dpp::Comm* C = ctx->comm;
   if (C && ctx->world > 1 && ctx->world <= dpp::kMaxIpcRanks && !getenv("DPP_NO_IPC")) {
     if (!C->mbox) {
-      DPP_CHECK(dpp::dev_alloc(ctx, &C->mbox, 2 * dpp::kMaxIpcRanks * dpp::kMboxEntry + 2));
-      DPP_CUDA(cudaMemset(C->mbox, 0, sizeof(double) * (2 * dpp::kMaxIpcRanks * dpp::kMboxEntry + 2)));
+      DPP_CHECK(dpp::dev_alloc(ctx, &C->mbox, 2 * dpp::kMaxIpcRanks * dpp::kMboxWords + 2));
+      DPP_CUDA(cudaMemset(C->mbox, 0, sizeof(double) * (2 * dpp::kMaxIpcRanks * dpp::kMboxWords + 2)));
     }
     if (cudaIpcGetMemHandle(&b.mbox_handle, C->mbox) == cudaSuccess) b.valid |= 1;
     else cudaGetLastError();

@@ -211,10 +211,13 @@ void cg_fused_destroy(dpp_context* ctx);
 // peer-memory (CUDA IPC) fast path, comm.cu
 constexpr int kMaxIpcRanks = 16;
 constexpr int kMboxEntry = 8;      // doubles per mailbox entry: 7 values + sequence flag
+constexpr int kMboxWords = 16;     // 8-byte words per entry: tagged-word protocol = 2 words per value (cg_device.cuh)
 struct IpcReduce {                 // kernel argument of the mailbox allreduce
-  double* local;                   // [2 slots][world][kMboxEntry]
+  double* local;                   // [2 slots][world][kMboxWords]
   double* peer[kMaxIpcRanks];      // the same array of every rank (peer[rank] == local)
   int rank, world;                 // world == 1: no exchange
+  int ll;                          // 1: tagged words (value = flag), 0: values + fence + flag word;
+                                   // measurement: 2 = no system fences at all, 3 = fence in every reduction
   unsigned long long* seq_dev;     // own device counter: number of exchanges executed so far
 };
 struct FoldArgs {                  // reduction epilogue folded into the producing kernel ("last block done")
@@ -229,6 +232,7 @@ struct IpcHalo {                   // kernel argument of the halo push (padded l
   double* peer_r[2];               // lower / upper neighbour's residual vector (null: none)
   long long peer_field[2];         // their padded field stride
   long long peer_ghost_off[2];     // offset of the ghost plane that mirrors my boundary plane
+  int debug_fence_all;             // DPP_DEBUG_FENCE_ALL: system fence in every block (measurement)
 };
 bool comm_ipc_ready(const dpp_context* ctx);        // mailbox all-reduce
 bool comm_ipc_halo_ready(const dpp_context* ctx);   // + halo push into the neighbours' residual vectors
