@@ -198,6 +198,27 @@ const double* dpp_solution_dev(dpp_handle h);
  * utils/manufactured_solutions.py:39-51 (2-D) / :82-88 (3-D) with the handle's parameters.  Single-GPU. */
 int dpp_error_norms(dpp_handle h, const double* u_host, const double* exact_host, int nq, double* out4);
 
+/* ---- post-processing: Darcy velocity (utils/postprocessing.py:34-63) ---------------- */
+
+/* calculate_darcy_velocity_from_pressure(pressure_field, conductivity): fd.project(-k grad(p_h), V^dim) on the
+ * pressure's own Lagrange space = one nodal-mass solve per component (Jacobi-CG to rtol, Firedrake's projection
+ * default is 1e-8).  p_host [n_nodes] scalar nodal pressure, or NULL for field `field` (0|1) of the last dpp_solve;
+ * velocity_host [dim * n_nodes], component-blocked (u_x of all nodes, then u_y, ...); iterations [dim] or NULL.
+ * Single-GPU. */
+int dpp_darcy_velocity(dpp_handle h, const double* p_host, int field, double conductivity, double rtol, int32_t max_it,
+                       double* velocity_host, int32_t* iterations);
+
+/* ---- spectrum estimates for the conditioning study (solvers/conditioning.py:105-218) ---- */
+
+/* `steps` Lanczos steps on the symmetric BC'd operator (which = 0: monolithic A_bc, 1: block A00, 2: block A11,
+ * the matrices get_matrix_data_from_form / iterative_bench.py:323-324 hand to calculate_condition_number), matrix-
+ * free, from a pseudo-random start vector (seed).  alpha_host, beta_host [steps]: diagonal and sub-diagonal of the
+ * Lanczos tridiagonal matrix, whose extreme eigenvalues converge to the extreme singular values of the (symmetric)
+ * operator; steps_done < steps when an invariant subspace was exhausted.  Replaces the dense SVD that caps the
+ * reference's 3-D study at N = 16.  Single-GPU. */
+int dpp_lanczos(dpp_handle h, int which, int32_t steps, uint64_t seed, double* alpha_host, double* beta_host,
+                int32_t* steps_done);
+
 /* ---- page-locked host buffers for results (full-rate D2H of the solution vector) -------------- */
 int dpp_host_alloc(void** ptr, int64_t bytes);   /* cudaMallocHost */
 int dpp_host_free(void* ptr);

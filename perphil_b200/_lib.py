@@ -83,6 +83,10 @@ _PROTOTYPES = {
     "dpp_kernel_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "dpp_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "dpp_error_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "dpp_darcy_velocity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int32, C.c_void_p,
+                                    C.c_void_p]),
+    "dpp_lanczos": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p,
+                             C.POINTER(C.c_int32)]),
     "dpp_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "dpp_host_free": (C.c_int, [C.c_void_p]),
 }

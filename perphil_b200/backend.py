@@ -217,6 +217,28 @@ class DppHandle:
         self._check(self._lib.dpp_error_norms(self._h, _ptr(uu), _ptr(ee), int(nq), _ptr(out)), "dpp_error_norms")
         return tuple(float(np.sqrt(v)) for v in out)
 
+    def darcy_velocity(self, conductivity: float, p: Optional[np.ndarray] = None, field: int = 0, rtol: float = 1e-8,
+                       max_it: int = 10000):
+        """L2 projection of -k grad(p_h) into V^dim: (velocity [dim, n_nodes], CG iterations per component).
+        p None = field `field` of the last solve's solution."""
+        pp = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
+        if pp is not None and pp.size != self.n_nodes:
+            raise ValueError("p must have n_nodes entries")
+        vel = np.empty((self.dim, self.n_nodes))
+        its = np.zeros(self.dim, dtype=np.int32)
+        self._check(self._lib.dpp_darcy_velocity(self._h, _ptr(pp), int(field), float(conductivity), float(rtol),
+                                                 int(max_it), _ptr(vel), _ptr(its)), "dpp_darcy_velocity")
+        return vel, its
+
+    def lanczos(self, steps: int, which: int = 0, seed: int = 0):
+        """(alpha, beta) of `steps` Lanczos steps on A_bc (which=0) or its diagonal block A00 (1) / A11 (2)."""
+        a = np.zeros(int(steps))
+        b = np.zeros(int(steps))
+        done = C.c_int32()
+        self._check(self._lib.dpp_lanczos(self._h, int(which), int(steps), int(seed), _ptr(a), _ptr(b), C.byref(done)),
+                    "dpp_lanczos")
+        return a[: done.value].copy(), b[: done.value].copy()
+
     def launch_count(self) -> int:
         n = C.c_int64()
         self._check(self._lib.dpp_kernel_launch_count(self._h, C.byref(n)), "dpp_kernel_launch_count")

@@ -520,6 +520,66 @@ int dpp_error_norms(dpp_handle ctx, const double* u_host, const double* exact_ho
   return dpp::error_norms(ctx, du, de, nq, out4);
 }
 
+int dpp_darcy_velocity(dpp_handle ctx, const double* p_host, int field, double conductivity, double rtol, int32_t max_it,
+                       double* velocity_host, int32_t* iterations) {
+  if (!ctx || !velocity_host || field < 0 || field > 1 || !(rtol > 0.0) || max_it < 1) return DPP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->world > 1) {
+    ctx->set_error("dpp_darcy_velocity: single-GPU handles only");
+    return DPP_ERR_INVALID;
+  }
+  if (!p_host && !ctx->d_solution) {
+    ctx->set_error("dpp_darcy_velocity: no solution on the device yet");
+    return DPP_ERR_STATE;
+  }
+  const int64_t n = ctx->n_nodes;
+  const int dim = ctx->dim;
+  double* buf = nullptr;   // [p | rhs (dim) | velocity (dim) | staging (dim)]
+  DPP_CUDA(cudaMalloc((void**)&buf, sizeof(double) * (size_t)(1 + 3 * dim) * n));
+  double *dp = buf, *drhs = buf + n, *dvel = buf + (1 + dim) * n, *dstage = buf + (1 + 2 * dim) * n;
+  int rc = DPP_OK;
+  auto run = [&]() -> int {
+    if (p_host) {
+      if (ctx->d_perm) {
+        DPP_CUDA(cudaMemcpyAsync(dstage, p_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        DPP_CHECK(dpp::perm_to_internal(ctx, dstage, dp, 1));
+      } else {
+        DPP_CUDA(cudaMemcpyAsync(dp, p_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+      }
+    } else {
+      DPP_CUDA(cudaMemcpyAsync(dp, ctx->d_solution + (size_t)field * n, sizeof(double) * n, cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+    }
+    DPP_CHECK(dpp::darcy_velocity(ctx, dp, conductivity, rtol, max_it, drhs, dvel, iterations, nullptr));
+    const double* src = dvel;
+    if (ctx->d_perm) {
+      for (int c = 0; c < dim; ++c) DPP_CHECK(dpp::perm_to_user(ctx, dvel + c * n, dstage + c * n, 1));
+      src = dstage;
+    }
+    DPP_CUDA(cudaMemcpyAsync(velocity_host, src, sizeof(double) * dim * n, cudaMemcpyDeviceToHost, ctx->stream));
+    DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DPP_OK;
+  };
+  rc = run();
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(buf);
+  return rc;
+}
+
+int dpp_lanczos(dpp_handle ctx, int which, int32_t steps, uint64_t seed, double* alpha_host, double* beta_host,
+                int32_t* steps_done) {
+  if (!ctx || !alpha_host || !beta_host || !steps_done || which < 0 || which > 2 || steps < 1) return DPP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->world > 1) {
+    ctx->set_error("dpp_lanczos: single-GPU handles only");
+    return DPP_ERR_INVALID;
+  }
+  int done = 0;
+  DPP_CHECK(dpp::krylov_lanczos(ctx, which, steps, seed, alpha_host, beta_host, &done));
+  *steps_done = done;
+  return DPP_OK;
+}
+
 int dpp_host_alloc(void** ptr, int64_t bytes) {
   if (!ptr || bytes <= 0) return DPP_ERR_INVALID;
   return cudaMallocHost(ptr, (size_t)bytes) == cudaSuccess ? DPP_OK : DPP_ERR_CUDA;

@@ -252,6 +252,10 @@ bool csr_valid(const dpp_context* ctx);
 void csr_destroy(dpp_context* ctx);
 
 // ---- numbering map helpers (dpp_api.cu): internal <-> caller numbering of field-blocked vectors
+// ---- darcy.cu / krylov.cu: post-processing and spectrum estimates
+int darcy_velocity(dpp_context* ctx, const double* d_p, double conductivity, double rtol, int max_it, double* d_rhs,
+                   double* d_vel, int32_t* iterations, double* residuals);
+int krylov_lanczos(dpp_context* ctx, int which, int steps, unsigned long long seed, double* alpha, double* beta, int* done);
 int perm_to_internal(dpp_context* ctx, const double* user, double* internal, int nf);
 int perm_to_user(dpp_context* ctx, const double* internal, double* user, int nf);
 

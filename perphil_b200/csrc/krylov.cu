@@ -46,6 +46,8 @@ struct OpSpec {
   int nf;      // 2: monolithic A_bc ; 1: block (row,col)
   int row, col;
   int mode;    // dpp_operator_mode
+  int kind = 0;        // 0: (block of) the DPP operator with Dirichlet elimination; 1: unconstrained nodal mass matrix (nf = 1)
+  int premasked = 1;   // inputs are exactly zero on eliminated rows (all Krylov vectors); 0: the apply masks them itself
 };
 
 struct Tol {
@@ -158,8 +160,13 @@ int apply_spec(dpp_context* ctx, const OpSpec& op, const double* x, double* y, b
   a.owned_end = ctx->owned_end;
   a.dot_partials = want_dot ? ctx->d_partials : nullptr;
   a.skip_flag = skip;
-  a.input_premasked = 1;  // Krylov vectors are exactly zero on eliminated rows/columns
-  if (op.nf == 2) {
+  a.input_premasked = op.premasked;  // Krylov vectors are exactly zero on eliminated rows/columns
+  if (op.kind == 1) {  // M x, no boundary conditions (L2 projections)
+    a.c = Coef{};
+    a.c.cM[0][0] = 1.0;
+    a.x[0] = x;
+    a.y[0] = y;
+  } else if (op.nf == 2) {
     a.c = dpp_coef(ctx);
     for (int f = 0; f < 2; ++f) {
       a.x[f] = x + f * n;
@@ -220,7 +227,7 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
   DPP_CHECK(vec_zero(ctx, x, len));
   DPP_CHECK(vec_copy(ctx, wk.r, b, len));
   const double* h = ctx->h_scalars + (size_t)slot * S_SLOT_SIZE;
-  if (fused && cg_fused_available(ctx, op.nf, op.mode, pc.type)) {
+  if (fused && op.kind == 0 && cg_fused_available(ctx, op.nf, op.mode, pc.type)) {
     // two kernels per iteration (cg_fused_uniform.cu): p, x updates live inside the apply kernel
     const Coef coef = op.nf == 2 ? dpp_coef(ctx) : block_coef(ctx, op.row, op.col);
     double* dtab = ctx->d_dtab + (size_t)slot * 16;
@@ -814,8 +821,95 @@ __global__ void k_fill_work(long long n, double* __restrict__ x, const uint8_t* 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     unsigned long long z = ((unsigned long long)i + salt) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     z ^= z >> 29; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 32;
-    x[i] = mask[i] ? 0.0 : (double)(z & 0xFFFFF) / 1048576.0 - 0.5;
+    x[i] = (mask != nullptr && mask[i]) ? 0.0 : (double)(z & 0xFFFFF) / 1048576.0 - 0.5;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// L2 projection solve M u = rhs on the scalar space (no boundary conditions): Jacobi-CG on the nodal mass
+// matrix, the linear solve inside fd.project (utils/postprocessing.py:63).  rhs / out: device, [n_nodes].
+// ------------------------------------------------------------------------------------------------
+int krylov_mass_solve(dpp_context* ctx, const double* d_rhs, double* d_out, double rtol, int max_it, int* its,
+                      double* rnorm, int* reason) {
+  DPP_CHECK(ensure_work(ctx));
+  Krylov* K = ctx->krylov;
+  const int64_t n = ctx->n_nodes;
+  // nodal mass diagonal (no masking) -> K->t[0..n), reciprocal -> K->t[n..2n)
+  Coef cm{};
+  cm.cM[0][0] = 1.0;
+  cm.cM[1][1] = 1.0;
+  uint8_t* save = ctx->d_mask;
+  ctx->d_mask = nullptr;
+  const int rc = (ctx->family == DPP_KERNEL_STRUCTURED) ? structured_diagonal(ctx, cm, K->t) : general_diagonal(ctx, cm, K->t);
+  ctx->d_mask = save;
+  DPP_CHECK(rc);
+  k_reciprocal<<<ew_blocks(ctx, n), 256, 0, ctx->stream>>>(n, K->t, K->t + n);
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  OpSpec op{1, 0, 0, DPP_OP_MATRIX_FREE, 1, 1};
+  Pc pc;
+  pc.type = DPP_PC_JACOBI;
+  pc.dinv = K->t + n;
+  Tol tol{rtol, 1e-300, 1e10, max_it};
+  KspOut o;
+  CgWork wk{K->ri, K->pi, K->wi, K->zi};
+  DPP_CHECK(cg_run(ctx, op, pc, d_rhs, d_out, wk, tol, 1, 4, 0, &o));
+  if (its) *its = o.its;
+  if (rnorm) *rnorm = o.rnorm;
+  if (reason) *reason = o.reason;
+  return DPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lanczos tridiagonalisation of the symmetric operator A_bc (which = 0), or of its diagonal blocks
+// A00 (1) / A11 (2), from a pseudo-random start vector that also has components on the eliminated rows
+// (their eigenvalue 1 belongs to the spectrum the reference's dense SVD sees, solvers/conditioning.py:
+// 105-218).  alpha[j] = <v_j, A v_j>, beta[j] = ||A v_j - alpha_j v_j - beta_{j-1} v_{j-1}||.  No
+// re-orthogonalisation: the extreme Ritz values, which is all a condition number needs, converge regardless.
+// ------------------------------------------------------------------------------------------------
+int krylov_lanczos(dpp_context* ctx, int which, int steps, unsigned long long seed, double* alpha, double* beta, int* done) {
+  if (!ctx->have_params) {
+    ctx->set_error("dpp_lanczos: call dpp_set_params first");
+    return DPP_ERR_STATE;
+  }
+  DPP_CHECK(ensure_work(ctx));
+  Krylov* K = ctx->krylov;
+  const int nf = which == 0 ? 2 : 1;
+  const int fld = which == 2 ? 1 : 0;
+  const int64_t n = ctx->n_nodes, len = nf * n;
+  const VecLayout L = layout(ctx, nf);
+  OpSpec op{nf, fld, fld, DPP_OP_MATRIX_FREE, 0, 0};
+  double *v = K->r, *vp = K->p, *w = K->w;
+  const double* h = ctx->h_scalars;   // slot 0
+  k_fill_work<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(len, v, nullptr, 7919ull * (seed + 1));
+  ctx->launches++;
+  DPP_CHECK(vec_zero(ctx, vp, len));
+  DPP_CHECK(vec_dot2(ctx, L, v, v, v, v, 0, POST_NONE));
+  DPP_CHECK(scalars_fetch(ctx, 0));
+  DPP_CHECK(vec_axpby(ctx, L, 0.0, v, 1.0 / std::sqrt(h[S_TMP]), v));
+  double b_prev = 0.0;
+  int j = 0;
+  for (; j < steps; ++j) {
+    int nb = 0;
+    DPP_CHECK(apply_spec(ctx, op, v, w, false, nullptr, &nb));
+    // (the kernels' fused <x, Ax> skips the identity rows, which are fixed up afterwards: separate dot)
+    DPP_CHECK(vec_dot2(ctx, L, v, w, v, w, 0, POST_NONE));
+    DPP_CHECK(scalars_fetch(ctx, 0));
+    const double a = h[S_TMP];
+    alpha[j] = a;
+    DPP_CHECK(vec_axpby(ctx, L, -a, v, 1.0, w));
+    if (j > 0) DPP_CHECK(vec_axpby(ctx, L, -b_prev, vp, 1.0, w));
+    DPP_CHECK(vec_dot2(ctx, L, w, w, w, w, 0, POST_NONE));
+    DPP_CHECK(scalars_fetch(ctx, 0));
+    const double b = std::sqrt(h[S_TMP]);
+    beta[j] = b;
+    if (!(b > 1e-14 * std::fabs(a))) { ++j; break; }   // invariant subspace found
+    DPP_CHECK(vec_axpby(ctx, L, 1.0 / b, w, 0.0, vp));   // vp <- next v
+    std::swap(v, vp);
+    b_prev = b;
+  }
+  *done = j;
+  return DPP_OK;
 }
 
 int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply_ms, double* update_ms,

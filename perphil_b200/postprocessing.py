@@ -1,14 +1,15 @@
 """Post-processing of a DPP solution (perphil.utils.postprocessing, utils/postprocessing.py:6-124):
-`split_dpp_solution`, `l2_error`, `h1_seminorm_error`.  The error integrals run on the GPU
-(csrc/error_norms.cu, `dpp_error_norms`); SURVEY 8(f) item 1.  The Darcy-velocity projection and the
-slicing helper of the reference stay out of scope (SURVEY 8f items 3+)."""
+`split_dpp_solution`, `calculate_darcy_velocity_from_pressure`, `l2_error`, `h1_seminorm_error`.  The error
+integrals (csrc/error_norms.cu, `dpp_error_norms`) and the Darcy-velocity projection
+(csrc/darcy.cu, `dpp_darcy_velocity`; item 3) run on the GPU.  The plotting/slicing helper of the reference
+(`slice_along_x`) stays out of scope."""
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 
-from .mesh import Expression, Function
+from .mesh import Expression, Function, _Dat
 
 
 def split_dpp_solution(dpp_solution: Function) -> Tuple[Function, Function]:
@@ -19,6 +20,50 @@ def split_dpp_solution(dpp_solution: Function) -> Tuple[Function, Function]:
     p1 = Function(W.sub(0), name="p1_h", val=np.array(dpp_solution.sub(0).dat.data, copy=True))
     p2 = Function(W.sub(1), name="p2_h", val=np.array(dpp_solution.sub(1).dat.data, copy=True))
     return p1, p2
+
+
+class VectorFunction:
+    """What `fd.Function(VectorFunctionSpace(mesh, "CG", p))` is to the callers of the projection: nodal
+    values `dat.data` of shape [n_nodes, dim] (Firedrake's layout for vector CG spaces)."""
+
+    def __init__(self, space, values: np.ndarray, name: str = "velocity"):
+        self._space = space
+        self.dat = _Dat(values)
+        self._name = name
+        self.cg_iterations = None
+
+    def function_space(self):
+        return self._space
+
+    def name(self):
+        return self._name
+
+    def sub(self, i: int) -> Function:
+        return Function(self._space, name=f"{self._name}[{i}]", val=np.array(self.dat.data[:, i], copy=True))
+
+
+def calculate_darcy_velocity_from_pressure(pressure_field: Function, conductivity, velocity_space=None,
+                                           degree: Optional[int] = None, rtol: float = 1e-8) -> VectorFunction:
+    """utils/postprocessing.py:34-63: project u = -k grad(p_h) into the vector CG space.  `conductivity` is a
+    float / Constant.  The velocity space is the vector version of the pressure's own Lagrange space (the
+    reference's default `degree=1` with its default degree-1 pressure space); another degree raises."""
+    from .solver import handle_for
+
+    V = pressure_field.function_space()
+    W = getattr(V, "parent", None)
+    if W is None:
+        raise ValueError("the pressure must live on W.sub(i) (use split_dpp_solution)")
+    h = handle_for(W)
+    p_deg = int(h.degree)
+    if degree is not None and int(degree) != p_deg:
+        raise NotImplementedError(f"velocity degree {degree} != pressure degree {p_deg}: the B200 projection uses "
+                                  "the pressure's own Lagrange space")
+    if velocity_space is not None and velocity_space is not V:
+        raise NotImplementedError("pass velocity_space=None (vector version of the pressure space)")
+    vel, its = h.darcy_velocity(float(conductivity), p=np.asarray(pressure_field.dat.data, dtype=np.float64), rtol=rtol)
+    out = VectorFunction(V, np.ascontiguousarray(vel.T), name="velocity")
+    out.cg_iterations = [int(i) for i in its]
+    return out
 
 
 def _norms(numerical: Function, exact, nq: int):

@@ -199,3 +199,39 @@ def test_approach_routing_follows_the_reference_harness():
     bcs = ex.default_bcs(V * V)
     assert len(bcs) == 2 and np.all(bcs[0].values() == 0.0)
     assert "time_KSPSolve" in ex.CSV_COLUMNS and "time_MatMult" in ex.CSV_COLUMNS
+
+
+def test_calculate_condition_number_matches_the_reference_table(golden):
+    """solvers/conditioning.py:105-218 semantics (dense SVD, zero_tol filter) on the oracle's assembled matrices:
+    conditioning_3d.csv N=4 and conditioning.csv N=8, including the macro/micro blocks."""
+    from oracle import dpp_oracle as orc
+    from perphil_b200.conditioning import calculate_condition_number
+
+    row = next(r for r in golden["conditioning_3d_hex_q1"] if r["N"] == 4)
+    osys = orc.build_system(orc.structured_mesh((4, 4, 4), 1), orc.Params(k1=1.0, k2=1e-2), "manufactured")
+    A = osys.A_bc.tocsr()
+    n = osys.n_nodes
+    assert abs(calculate_condition_number(A, None) - row["cond_monolithic"]) < 1e-9 * row["cond_monolithic"]
+    assert abs(calculate_condition_number(A[:n, :n], 0) - row["cond_macro"]) < 1e-9 * row["cond_macro"]
+    assert abs(calculate_condition_number(A[n:, n:], n) - row["cond_micro"]) < 1e-9 * row["cond_micro"]
+    # sparse route (ARPACK at both ends) agrees to its tolerance
+    ks = calculate_condition_number(A, 6, use_sparse=True)
+    assert abs(ks - row["cond_monolithic"]) < 1e-5 * row["cond_monolithic"]
+    import scipy.sparse as sp
+
+    assert np.isnan(calculate_condition_number(sp.csr_matrix((0, 0)), None))
+
+
+def test_oracle_darcy_projection_reproduces_polynomial_gradients():
+    """Galerkin projection of -k grad(p_h): exact whenever grad(p_h) lies in the space (Q1: linear p; Q2:
+    p = x^2 + xy)."""
+    from oracle import dpp_oracle as orc
+
+    m = orc.structured_mesh((4, 5, 3), 1)
+    X = m.coords
+    v = orc.darcy_velocity(m, 2 * X[:, 0] - 3 * X[:, 1] + 0.5 * X[:, 2], 2.0)
+    assert np.abs(v - np.array([-4.0, 6.0, -1.0])[:, None]).max() < 1e-12
+    m = orc.structured_mesh((3, 4), 2)
+    X = m.coords
+    v = orc.darcy_velocity(m, X[:, 0] ** 2 + X[:, 0] * X[:, 1], 1.0)
+    assert np.abs(v[0] + 2 * X[:, 0] + X[:, 1]).max() < 1e-12 and np.abs(v[1] + X[:, 0]).max() < 1e-12
