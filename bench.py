@@ -287,7 +287,7 @@ def main():
         "solve_roofline": {"achieved": solve_gbs, "peak": peak, "unit": "GB/s", "frac": solve_gbs / peak,
                            "bytes_per_iteration": iter_bytes},
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # reported on rank 0 at N=1 only
         line["cpu_baseline"] = cpu_baseline(args.cpu_size)
     print(json.dumps(line))
 

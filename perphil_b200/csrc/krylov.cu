@@ -36,6 +36,8 @@ struct Krylov {
   double* d_gm = nullptr;        // device-resident GMRES state (gmres_run_device)
   double* h_gm = nullptr;        // pinned mirror of its scalar head
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* h_poll = nullptr;      // pinned [2][S_SLOT_SIZE]: scalar snapshots behind each CG batch (cg_run)
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr};
   int64_t inner_its = 0;
   int64_t apply_count = 0;
 };
@@ -251,12 +253,36 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
     // sequences -> replayed as one CUDA graph after the first (directly launched) batch
     unsigned long long key = mix(mix(mix(ctx->state_gen, (unsigned long long)op.nf * 16 + op.row * 4 + pc.type),
                                      (unsigned long long)every), (unsigned long long)(uintptr_t)hist_device(ctx, slot));
-    while (h[S_REASON] == 0.0) {
+    // Polling without a pipeline bubble: batch k+1 is enqueued BEFORE the host waits for the scalars of
+    // batch k (copied into a pinned double buffer behind each batch).  Kernels launched past convergence
+    // are no-ops on every rank alike (all ranks hold bit-identical scalars), so the speculative batch
+    // changes nothing; it costs a few microseconds once per solve instead of a host round trip per batch.
+    Krylov* K = ctx->krylov;
+    if (!K->h_poll) {
+      DPP_CUDA(cudaMallocHost((void**)&K->h_poll, sizeof(double) * 2 * S_SLOT_SIZE));
+      for (auto& e : K->ev_poll) DPP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    auto enqueue = [&](int b) -> int {
       if (kk == 0 || (every & 1)) DPP_CHECK(batch(kk));
-      else DPP_CHECK(run_graphed(ctx, ctx->krylov->cg_graph[slot], key, [&]() { return batch(kk); }));
+      else DPP_CHECK(run_graphed(ctx, K->cg_graph[slot], key, [&]() { return batch(kk); }));
       kk += every;
-      ctx->krylov->apply_count += every;
-      DPP_CHECK(scalars_fetch(ctx, slot));
+      DPP_CUDA(cudaMemcpyAsync(K->h_poll + (size_t)b * S_SLOT_SIZE, S, sizeof(double) * S_SLOT_SIZE, cudaMemcpyDeviceToHost,
+                               ctx->stream));
+      DPP_CUDA(cudaEventRecord(K->ev_poll[b], ctx->stream));
+      return DPP_OK;
+    };
+    if (h[S_REASON] == 0.0) {
+      int cur = 0;
+      DPP_CHECK(enqueue(cur));
+      K->apply_count += every;
+      while (true) {
+        DPP_CHECK(enqueue(cur ^ 1));   // speculative
+        DPP_CUDA(cudaEventSynchronize(K->ev_poll[cur]));
+        if (K->h_poll[(size_t)cur * S_SLOT_SIZE + S_REASON] != 0.0) break;
+        K->apply_count += every;       // the batch just enqueued was needed
+        cur ^= 1;
+      }
+      DPP_CHECK(scalars_fetch(ctx, slot));   // final state (also drains the speculative no-op batch)
     }
     DPP_CHECK(cg_fused_x_finalize(ctx, op.nf, (long long)h[S_ITS], slot, x));
     out->its = (int)h[S_ITS];
@@ -1092,6 +1118,9 @@ void krylov_destroy(dpp_context* ctx) {
     if (gsl->exec) cudaGraphExecDestroy(gsl->exec);
   if (K->d_gm) cudaFree(K->d_gm);
   if (K->h_gm) cudaFreeHost(K->h_gm);
+  if (K->h_poll) cudaFreeHost(K->h_poll);
+  for (auto& e : K->ev_poll)
+    if (e) cudaEventDestroy(e);
   for (auto& e : K->ev)
     if (e) cudaEventDestroy(e);
   delete K;
