@@ -406,13 +406,21 @@ struct RArgs {
   IpcHalo halo;              // peer residual vectors: boundary planes are stored there as well
 };
 
-constexpr int UNROLL = 4;
+constexpr int UNROLL = 4;   // pairs of nodes per thread and loop trip: 2 arrays x 4 x 16 B = 128 B in flight per thread
 
 __device__ __forceinline__ void push_halo(const RArgs& a, int f, long long q, double v) {
   if (a.halo.peer_r[0] != nullptr && q < a.ob + a.plane)
     a.halo.peer_r[0][f * a.halo.peer_field[0] + a.halo.peer_ghost_off[0] + (q - a.ob)] = v;
   if (a.halo.peer_r[1] != nullptr && q >= a.oe - a.plane)
     a.halo.peer_r[1][f * a.halo.peer_field[1] + a.halo.peer_ghost_off[1] + (q - (a.oe - a.plane))] = v;
+}
+// the same for an aligned pair (q even; a pair never straddles a plane: planes hold an even number of doubles)
+__device__ __forceinline__ void push_halo2(const RArgs& a, int f, long long q, double2 v) {
+  if (a.halo.peer_r[0] != nullptr && q < a.ob + a.plane)
+    *reinterpret_cast<double2*>(a.halo.peer_r[0] + f * a.halo.peer_field[0] + a.halo.peer_ghost_off[0] + (q - a.ob)) = v;
+  if (a.halo.peer_r[1] != nullptr && q >= a.oe - a.plane)
+    *reinterpret_cast<double2*>(a.halo.peer_r[1] + f * a.halo.peer_field[1] + a.halo.peer_ghost_off[1] +
+                                (q - (a.oe - a.plane))) = v;
 }
 
 __device__ __forceinline__ int node_class(const RArgs& a, unsigned q) {
@@ -426,8 +434,11 @@ __device__ __forceinline__ int node_class(const RArgs& a, unsigned q) {
   return bx + by + bz;
 }
 
+// Streaming kernel: every thread walks its block's range in aligned PAIRS of nodes (16-byte loads and stores;
+// the padded pitch is a multiple of 16 doubles, so a pair never leaves its row) and keeps the lattice
+// position (i, j, k) of its pair incrementally -- one magic division per thread, not per node.
 template <bool INIT>
-__global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
+__global__ void __launch_bounds__(VT, 3) k_cg_r_update(const RArgs a) {
   __shared__ double sm[kFinishSmem];
   __shared__ double tab[16];
   __shared__ int last_flag;
@@ -437,8 +448,8 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
   if (threadIdx.x < 16) tab[threadIdx.x] = (threadIdx.x < 8 * a.nf) ? a.dtab[threadIdx.x] : 1.0;
   __syncthreads();
   const double alpha = INIT ? 0.0 : a.S[S_ALPHA];
-  const long long nown = a.oe - a.ob;
-  const long long per = (nown + gridDim.x - 1) / gridDim.x;
+  const long long nown = a.oe - a.ob;                                      // even (whole padded planes)
+  const long long per = 2 * ((nown / 2 + gridDim.x - 1) / gridDim.x);      // even share per block
   const long long b = (long long)blockIdx.x * per;
   const long long e = b + per < nown ? b + per : nown;
   const int f = blockIdx.y;
@@ -446,41 +457,65 @@ __global__ void __launch_bounds__(VT) k_cg_r_update(const RArgs a) {
   const double* wf = INIT ? nullptr : a.w + (long long)f * a.field;
   const double* tf = tab + f * 8;
   const bool zc = a.zero_class[f] != 0;
+  const bool xdim = a.ni > 1;
   double srz = 0.0, szz = 0.0;
-  long long q = a.ob + b + threadIdx.x;
+  long long q = a.ob + b + 2 * threadIdx.x;
   const long long qe = a.ob + (e > b ? e : b);
-  for (; q + (UNROLL - 1) * VT < qe; q += UNROLL * VT) {
-    double rv[UNROLL], wv[UNROLL];
+  // lattice position of the pair at q
+  unsigned k, j, i;
+  {
+    const unsigned qq = (unsigned)(q < qe ? q : a.ob);
+    const unsigned t = (unsigned)(((unsigned long long)qq * a.mag_k) >> a.sh_k);   // q / pitch
+    k = qq - t * a.pitch;
+    i = (unsigned)(((unsigned long long)t * a.mag_j) >> a.sh_j);                   // t / nj
+    j = t - i * a.nj;
+  }
+  auto advance = [&]() {   // position of the pair 2*VT doubles further on
+    k += 2 * VT;
+    while (k >= a.pitch) {
+      k -= a.pitch;
+      if (++j == a.nj) { j = 0; ++i; }
+    }
+  };
+  auto classes = [&](int& c0, int& c1) {
+    const int bx = (xdim && ((i == 0 && a.dom_lo) || (i == a.ni - 1 && a.dom_hi))) ? 4 : 0;
+    const int bxy = bx + ((j == 0 || j == a.nj - 1) ? 2 : 0);
+    c0 = bxy + ((k == 0 || k == a.nk - 1) ? 1 : 0);
+    c1 = bxy + ((k + 1 == a.nk - 1) ? 1 : 0);
+  };
+  auto one = [&](long long qq, double2 rv, double2 wv) {
+    int c0, c1;
+    classes(c0, c1);
+    double2 rn = rv;
+    if (!INIT) {
+      rn.x = (zc && c0) ? 0.0 : fma(-alpha, wv.x, rv.x);
+      rn.y = (zc && c1) ? 0.0 : fma(-alpha, wv.y, rv.y);
+      *reinterpret_cast<double2*>(rf + qq) = rn;
+      push_halo2(a, f, qq, rn);
+    }
+    const double z0 = tf[c0] * rn.x, z1 = tf[c1] * rn.y;
+    srz = fma(rn.x, z0, srz);
+    szz = fma(z0, z0, szz);
+    srz = fma(rn.y, z1, srz);
+    szz = fma(z1, z1, szz);
+  };
+  for (; q + (UNROLL - 1) * 2 * VT < qe; q += UNROLL * 2 * VT) {
+    double2 rv[UNROLL], wv[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      rv[u] = rf[q + u * VT];
-      wv[u] = INIT ? 0.0 : wf[q + u * VT];
+      rv[u] = *reinterpret_cast<const double2*>(rf + q + u * 2 * VT);
+      wv[u] = INIT ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(wf + q + u * 2 * VT);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      double rn = rv[u];
-      const int cls = node_class(a, (unsigned)(q + u * VT));
-      if (!INIT) {
-        rn = (zc && cls) ? 0.0 : fma(-alpha, wv[u], rv[u]);
-        rf[q + u * VT] = rn;
-        push_halo(a, f, q + u * VT, rn);
-      }
-      const double zv = tf[cls] * rn;
-      srz = fma(rn, zv, srz);
-      szz = fma(zv, zv, szz);
+      one(q + u * 2 * VT, rv[u], wv[u]);
+      advance();
     }
   }
-  for (; q < qe; q += VT) {
-    double rn = rf[q];
-    const int cls = node_class(a, (unsigned)q);
-    if (!INIT) {
-      rn = (zc && cls) ? 0.0 : fma(-alpha, wf[q], rn);
-      rf[q] = rn;
-      push_halo(a, f, q, rn);
-    }
-    const double zv = tf[cls] * rn;
-    srz = fma(rn, zv, srz);
-    szz = fma(zv, zv, szz);
+  for (; q < qe; q += 2 * VT) {
+    one(q, *reinterpret_cast<const double2*>(rf + q),
+        INIT ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(wf + q));
+    advance();
   }
   const double t0 = block_sum(srz, sm);
   const double t1 = block_sum(szz, sm);
@@ -897,9 +932,18 @@ static int make_rargs(dpp_context* ctx, FusedState* F, int nf, int slot, const d
 }
 
 static int r_blocks(const dpp_context* ctx, const RArgs& a) {
+  // one wave of resident blocks (occupancy from the driver: 3 blocks of 256 threads per SM at 78 registers),
+  // at least two loop trips of UNROLL pairs per thread; DPP_RUPD_WAVES: measurement override
+  static int occ = 0;
+  if (occ == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_r_update<false>, VT, 0) != cudaSuccess || occ < 1) occ = 3;
+  }
+  int waves = 1;
+  if (const char* e = getenv("DPP_RUPD_WAVES")) waves = std::max(1, atoi(e));
   const long long nown = a.oe - a.ob;
-  long long want = (nown + (long long)VT * UNROLL * 4 - 1) / ((long long)VT * UNROLL * 4);
-  const long long cap = std::max(1, (ctx->sm_count * 8) / std::max(1, a.nf));
+  const long long trip = 2LL * VT * UNROLL;
+  long long want = (nown + 2 * trip - 1) / (2 * trip);
+  const long long cap = std::max(1, (ctx->sm_count * occ * waves) / std::max(1, a.nf));
   return (int)std::max(1LL, std::min(std::min(want, cap), (long long)kMaxPartialBlocks / 2));
 }
 
