@@ -159,7 +159,7 @@ constexpr int kNumScalars = 256;
 // hardware in linear order (tile fastest), so all tiles of a segment run concurrently (halo rows/columns
 // of neighbouring tiles then hit in L2 -- a fully persistent partition loses that, measured: 2x DRAM
 // reads).  Cost model: rounds of `capacity` resident CTAs x (planes per segment + 2 redundant planes +
-// prologue); returns the segment count with the smallest cost.
+// prologue + drift penalty); returns the segment count with the smallest cost.
 inline int choose_x_segments(int tiles, int nown, int capacity, int max_ctas, int redundant = 2) {
   int best = 1;
   long long best_cost = -1;
@@ -168,7 +168,10 @@ inline int choose_x_segments(int tiles, int nown, int capacity, int max_ctas, in
     const int len = (nown + nseg - 1) / nseg;
     if (len < 4 && nseg > 1) break;
     const long long rounds = ((long long)tiles * nseg + capacity - 1) / capacity;
-    const long long cost = rounds * (len + redundant + 2);
+    // long runs let neighbouring tiles drift apart (no synchronisation between CTAs): beyond ~32 planes their
+    // halo rows/columns start to miss in L2 (measured at 256^3: 2 segments of 128 planes 327 us, 9 of 29 303 us)
+    const long long drift = len > 32 ? (len - 32) / 4 : 0;
+    const long long cost = rounds * (len + redundant + 2 + drift);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nseg; }
   }
   return best;

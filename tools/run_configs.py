@@ -13,7 +13,7 @@ if world > 1:
     comm = SlabComm.from_env()
     torch.cuda.set_device(comm.device)
 rank = comm.rank if comm else 0
-want = [a if a == "4w" else int(a) for a in sys.argv[1:]] or [1, 2, 4, 5]
+want = [a if a in ("4w", "2s") else int(a) for a in sys.argv[1:]] or [1, 2, 4, 5]
 out = []
 
 
@@ -69,6 +69,10 @@ if 1 in want and world == 1:
 if 2 in want:
     run(f"2: 3D hex Q1 {N2}^3, CG + block-Jacobi (additive) fieldsplit", (N2,) * 3, 1, "B200_CG_FIELDSPLIT_PARAMS")
     run(f"2: 3D hex Q1 {N2}^3, Jacobi-CG", (N2,) * 3, 1, "B200_CG_JACOBI_PARAMS")
+if "2s" in want:   # configs[1]: "scaled 8^3 -> 128^3, CG + block-Jacobi fieldsplit on 1 B200"
+    for n in (8, 16, 32, 64, 128):
+        run(f"2 sweep: 3D hex Q1 {n}^3, CG + block-Jacobi (additive) fieldsplit", (n,) * 3, 1, "B200_CG_FIELDSPLIT_PARAMS")
+        run(f"2 sweep: 3D hex Q1 {n}^3, Jacobi-CG", (n,) * 3, 1, "B200_CG_JACOBI_PARAMS")
 if 4 in want:
     run(f"4: 3D hex Q2 {N4}^3, block Picard (scale splitting), Jacobi-CG blocks", (N4,) * 3, 2, "B200_PICARD_SPLIT_PARAMS",
         nonlinear=True, repeats=2 if world > 1 else 1)
