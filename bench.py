@@ -25,7 +25,7 @@ import numpy as np
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/): filled in after each profiling pass, None until a capture of the current kernel exists.
-TRAFFIC_NCU = {"fused_apply": 894369024 + 786148864}   # profiles/r01_fused_tma2_kernels.md (256^3)
+TRAFFIC_NCU = {"fused_apply": 1648143872, "r_update": 819625216}   # profiles/r01_cg_kernels_final2.md (256^3)
 
 
 def measured_peaks():

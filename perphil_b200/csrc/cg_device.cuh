@@ -106,11 +106,39 @@ __device__ __forceinline__ void finish_reduction(const double* __restrict__ part
   double* recv = sm + VT / 32 + kMboxEntry + 2;   // [world][kMboxEntry - 1]
   const int tid = threadIdx.x + threadIdx.y * blockDim.x;
   if (tid == 0) *timed_out = 0;
-  for (int w = 0; w < width; ++w) {
-    double v = 0.0;
-    for (int b = tid; b < nblocks; b += VT) v += partials[(size_t)b * width + w];
-    const double t = block_sum(v, sm);
-    if (tid == 0) vals[w] = t;
+  if (width == 2) {   // both sums in one pass (the r-update epilogue sits on the critical path of every iteration)
+    double v0 = 0.0, v1 = 0.0;
+    for (int b = tid; b < nblocks; b += VT) {
+      const double2 pv = *reinterpret_cast<const double2*>(partials + (size_t)b * 2);
+      v0 += pv.x;
+      v1 += pv.y;
+    }
+    v0 = warp_sum(v0);
+    v1 = warp_sum(v1);
+    const int lane = tid & 31, wid = tid >> 5;
+    __syncthreads();
+    if (lane == 0) {
+      sm[wid] = v0;
+      recv[wid] = v1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int w = 0; w < VT / 32; ++w) {
+        t0 += sm[w];
+        t1 += recv[w];
+      }
+      vals[0] = t0;
+      vals[1] = t1;
+    }
+  } else {
+    for (int w = 0; w < width; ++w) {
+      double v = 0.0;
+      for (int b = tid; b < nblocks; b += VT) v += partials[(size_t)b * width + w];
+      const double t = block_sum(v, sm);
+      if (tid == 0) vals[w] = t;
+    }
   }
   const bool dist = ipc.world > 1;
   unsigned long long* seq_sm = reinterpret_cast<unsigned long long*>(sm + VT / 32 + kMboxEntry + 1);

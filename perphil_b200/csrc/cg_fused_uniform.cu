@@ -24,6 +24,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <utility>
 
@@ -833,6 +834,13 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
   }
   s.ntk = (((s.k_hi + 1) >> 1) - (s.k_lo >> 1) + TK / 2 - 1) / (TK / 2);   // tiles hold <= TK/2 column pairs
   s.ntj = (s.j_hi - s.j_lo + TJ - 1) / TJ;
+  if (const char* e = getenv("DPP_FUSED_TILES")) {   // measurement override "ntj,ntk" (>= the minimal counts)
+    int tj = 0, tk = 0;
+    if (sscanf(e, "%d,%d", &tj, &tk) == 2) {
+      s.ntj = std::max(s.ntj, tj);
+      s.ntk = std::max(s.ntk, tk);
+    }
+  }
   const int tiles = s.ntk * s.ntj;
   const int nown = s.i_end - s.i_begin;
   if (nown <= 0) { *n_partial_blocks = 0; return DPP_OK; }

@@ -30,7 +30,7 @@ def launches(path, out):
     with open(out, "w") as f:
         f.write(f"# ncu launch list summary ({path.split('/')[-1]})\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` over a window of the timed solve of "
-                "`python bench.py --steps 1 --warmup 1 --no-cpu` (256^3, Jacobi-CG). Per-launch times are cold-cache and "
+                "`python bench.py --steps 1 --warmup 3 --no-cpu` (256^3, Jacobi-CG; `-s 1500 -c 400`). Per-launch times are cold-cache and "
                 "serialised: read the SHARE column.\n\n")
         f.write("| kernel | launches | total us | mean us | share |\n|---|---:|---:|---:|---:|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
