@@ -200,11 +200,12 @@ def main():
         sampler.start()
     l0 = h.launch_count()
     barrier()
-    dev_ms = []
+    dev_ms, setup_ms = [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         _, si = h.solve(opt, want_solution=False)
         dev_ms.append(si.setup_ms + si.solve_ms)
+        setup_ms.append(si.setup_ms)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     launches = h.launch_count() - l0
@@ -268,6 +269,7 @@ def main():
                    "preset": "B200_CG_JACOBI_PARAMS", "iterations": its, "parallelism": f"slab x{world}" + (" peer-memory halo + mailbox allreduce" if h.info().peer_memory == 3 else (" NCCL" if world > 1 else "")),
                    "kernel_family": "structured" if structured else "general"},
         "iterations": its, "residual_error": sol.residual_error, "wall_ms_per_step": wall_ms,
+        "lifting_setup_ms": float(np.mean(setup_ms)), "krylov_us_per_iteration": (ms - float(np.mean(setup_ms))) / its * 1e3,
         "tts_mdofs": ndof / (ms * 1e-3) / 1e6,
         "matvec_gdofs": ndof / ((mv_ms if fused else apply_ms) * 1e-3) / 1e9, "matvec_ms": mv_ms if fused else apply_ms,
         "matvec_gbs": apply_bytes / ((mv_ms if fused else apply_ms) * 1e-3) / 1e9 / world,
