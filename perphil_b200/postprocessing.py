@@ -1,8 +1,8 @@
 """Post-processing of a DPP solution (perphil.utils.postprocessing, utils/postprocessing.py:6-124):
 `split_dpp_solution`, `calculate_darcy_velocity_from_pressure`, `l2_error`, `h1_seminorm_error`.  The error
 integrals (csrc/error_norms.cu, `dpp_error_norms`) and the Darcy-velocity projection
-(csrc/darcy.cu, `dpp_darcy_velocity`; item 3) run on the GPU.  The plotting/slicing helper of the reference
-(`slice_along_x`) stays out of scope."""
+(csrc/darcy.cu, `dpp_darcy_velocity`; item 3) run on the GPU; `slice_along_x` (a plotting helper: point evaluation
+along a line) is host numpy."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -64,6 +64,35 @@ def calculate_darcy_velocity_from_pressure(pressure_field: Function, conductivit
     out = VectorFunction(V, np.ascontiguousarray(vel.T), name="velocity")
     out.cg_iterations = [int(i) for i in its]
     return out
+
+
+def slice_along_x(scalar_field: Function, x_value: float) -> Tuple[np.ndarray, np.ndarray]:
+    """utils/postprocessing.py:66-86: sample a scalar field along the vertical line x = x_value, at the distinct
+    y-coordinates of the space's nodes (`np.unique` of the interpolated y coordinate there) -- the
+    `scalar_field.at((x, y))` point evaluation of the reference, done on the host for the 2-D tensor-product
+    spaces of this package (a plotting helper, not part of the GPU path)."""
+    V = scalar_field.function_space()
+    mesh = V.mesh()
+    if mesh.dim != 2:
+        raise NotImplementedError("slice_along_x samples 2-D fields (the reference uses it for the 2-D notebooks)")
+    p = int(V.degree)
+    ax, ay = mesh.local_axes(p)
+    nx, ny = V.grid_nodes
+    u = np.asarray(scalar_field.dat.data, dtype=float).reshape(nx, ny)
+    xv = ax[::p]                                   # vertex coordinates along x
+    if not (xv[0] - 1e-14 <= x_value <= xv[-1] + 1e-14):
+        raise ValueError(f"x = {x_value} is outside the mesh")
+    c = int(min(max(np.searchsorted(xv, x_value, side="right") - 1, 0), xv.size - 2))
+    xi = (x_value - xv[c]) / (xv[c + 1] - xv[c])
+    nodes = np.linspace(0.0, 1.0, p + 1)
+    vals = np.zeros(ny)
+    for a in range(p + 1):
+        N = 1.0
+        for m in range(p + 1):
+            if m != a:
+                N *= (xi - nodes[m]) / (nodes[a] - nodes[m])
+        vals += N * u[p * c + a, :]
+    return np.asarray(ay, dtype=float).copy(), vals
 
 
 def _norms(numerical: Function, exact, nq: int):

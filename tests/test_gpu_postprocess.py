@@ -128,3 +128,19 @@ def test_lanczos_tridiagonal_is_a_projection_of_the_operator():
     e1 = pb.condition_number_matrix_free(pb.dpp_form(W2, prm2)[0], bcs2, rtol=1e-6)
     assert e1.converged and e1.condition_number > 3305.0   # kappa(N=32) > kappa(N=16) of the stored table
     pb.release_handles()
+
+
+def test_slices_at_x_half_match_the_notebook(golden):
+    """`slice_along_x(p_h, 0.5)` of the B200 solution on the 10x10 quad mesh reproduces the values the
+    operator-splitting notebook prints for the monolithic LU solve (ipynb cell 15: p1_h, p2_h at 11 y-values),
+    through the reference's own call sequence solve_dpp -> split_dpp_solution -> slice_along_x."""
+    g = golden["operator_splitting_notebook_10x10"]
+    W, prm, bcs, _ = make_problem((10, 10), 1)
+    sol = pb.solve_dpp(W, prm, bcs, solver_parameters={**pb.B200_CG_JACOBI_PARAMS, "ksp_rtol": 1e-13})
+    p1, p2 = pb.split_dpp_solution(sol.solution)
+    y_ref, p1_ref, p2_ref = g["slice_x0.5_monolithic_lu"]
+    y, v1 = pb.slice_along_x(p1, 0.5)
+    _, v2 = pb.slice_along_x(p2, 0.5)
+    assert np.allclose(y, y_ref)
+    assert np.allclose(v1, p1_ref, rtol=2e-8) and np.allclose(v2, p2_ref, rtol=2e-8)
+    pb.release_handles()

@@ -235,3 +235,19 @@ def test_oracle_darcy_projection_reproduces_polynomial_gradients():
     X = m.coords
     v = orc.darcy_velocity(m, X[:, 0] ** 2 + X[:, 0] * X[:, 1], 1.0)
     assert np.abs(v[0] + 2 * X[:, 0] + X[:, 1]).max() < 1e-12 and np.abs(v[1] + X[:, 0]).max() < 1e-12
+
+
+def test_slice_along_x_is_point_evaluation_of_the_fe_function():
+    """utils/postprocessing.py:66-86: values at (x, y_j) for the distinct node ordinates y_j; exact for fields
+    the space represents (Q1: bilinear, Q2: biquadratic), also off the node lines."""
+    for deg in (1, 2):
+        mesh = pb.UnitSquareMesh(5, 4)
+        _, V = pb.create_function_spaces(mesh, pressure_deg=deg)
+        X = V.node_coordinates
+        f = pb.Function(V, val=2.0 * X[:, 0] ** deg + 3.0 * X[:, 1] * X[:, 0])
+        for x in (0.0, 0.37, 0.6, 1.0):
+            y, v = pb.slice_along_x(f, x)
+            assert y.size == deg * 4 + 1
+            assert np.abs(v - (2.0 * x ** deg + 3.0 * y * x)).max() < 1e-13
+    with pytest.raises(ValueError):
+        pb.slice_along_x(f, 1.5)
