@@ -224,7 +224,7 @@ class DppHandle:
         pp = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
         if pp is not None and pp.size != self.n_nodes:
             raise ValueError("p must have n_nodes entries")
-        vel = np.empty((self.dim, self.n_nodes))
+        vel = PINNED.take(self.dim * self.n_nodes).reshape(self.dim, self.n_nodes)   # page-locked: full-rate D2H
         its = np.zeros(self.dim, dtype=np.int32)
         self._check(self._lib.dpp_darcy_velocity(self._h, _ptr(pp), int(field), float(conductivity), float(rtol),
                                                  int(max_it), _ptr(vel), _ptr(its)), "dpp_darcy_velocity")
