@@ -295,6 +295,7 @@ int dpp_comm_ipc_export(dpp_handle ctx, void* blob_out) {
     if (!C->mbox) {
       DPP_CHECK(dpp::dev_alloc(ctx, &C->mbox, 2 * dpp::kMaxIpcRanks * dpp::kMboxWords + 2));
       DPP_CUDA(cudaMemset(C->mbox, 0, sizeof(double) * (2 * dpp::kMaxIpcRanks * dpp::kMboxWords + 2)));
+      DPP_CUDA(cudaDeviceSynchronize());   // the zeros are in place before any peer can learn the handle
     }
     if (cudaIpcGetMemHandle(&b.mbox_handle, C->mbox) == cudaSuccess) b.valid |= 1;
     else cudaGetLastError();
