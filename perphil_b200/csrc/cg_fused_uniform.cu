@@ -135,9 +135,11 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     for (int q = 0; q < RING; ++q) mbar_init(mbar0 + 8 * q, 1);
     fence_mbar_init();
   }
+  // the class table is written once per solve, before the first kernel of the iteration: safe to fetch while
+  // the previous kernel of the stream is still in its reduction epilogue
+  if (tid < 16) sm.dtab[tid] = (FUSED && tid < 8 * NF) ? s.dtab[tid] : 1.0;
   pdl_wait();  // everything below reads what the previous kernel of the stream produced
   if (FUSED && s.S[S_REASON] != 0.0) return;
-  if (tid < 16) sm.dtab[tid] = (FUSED && tid < 8 * NF) ? s.dtab[tid] : 1.0;
   // scalars of the iteration (device resident; written by the reduction epilogues)
   double beta = 0.0, alpha_prev = 0.0;
   bool xpend = false;
@@ -184,6 +186,25 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     const int pw_lo = (i_lo == s.i_begin && s.i_begin > 0) ? i_lo - 1 : i_lo;
     const int pw_hi = (i_hi == s.i_end && s.i_end < ni) ? i_hi + 1 : i_hi;
 
+    // producer (one thread): fetch plane PL into ring slot SL
+#define DPP_ISSUE(SL, PL)                                                                              \
+  if (tid == 0) {                                                                                      \
+    const bool xin = FUSED && xpend && (PL) >= i_lo && (PL) < i_hi;                                    \
+    const unsigned mb = mbar0 + 8 * (SL);                                                              \
+    fence_proxy_async();                                                                               \
+    mbar_expect_tx(mb, (unsigned)((FUSED ? 2 : 1) * NF * SLOT * 8 + (xin ? NF * XSLOT * 8 : 0)));      \
+    if (FUSED) tma_load_4d(sr_base + (SL)*RS * 8, &tm_r, mb, k0 - 2, j0 - 1, (PL), 0);                 \
+    tma_load_4d(sp_base + (SL)*RS * 8, &tm_p, mb, k0 - 2, j0 - 1, (PL), 0);                            \
+    if (xin) tma_load_4d(sx_base + (SL)*NF * XSLOT * 8, &tm_x, mb, k0, j0, (PL), 0);                   \
+  }
+
+    // first two planes of the run are requested before the coefficient set-up below (which then overlaps the
+    // load latency instead of preceding it)
+    __syncthreads();  // the ring is free: every thread finished the previous run
+    DPP_ISSUE(2, i_first)
+    if (i_first + 1 <= i_hi) DPP_ISSUE(0, i_first + 1)
+
+
     // the elements this thread combines: its two nodes + at most one node of the halo ring
     constexpr int HW = TK + 2;               // width of the halo ring (nodes k0-1 .. k0+TK)
     constexpr int HALO = 2 * HW + 2 * TJ;
@@ -204,18 +225,6 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     const int clsH = ((jH == 0 || jH == nj - 1) ? 2 : 0) + ((kH == 0 || kH == nk - 1) ? 1 : 0);
 
     long long off_c = (long long)i_first * plane + (long long)jA * pitch + k;  // node A in the plane being combined
-
-    // producer (one thread): fetch plane PL into ring slot SL
-#define DPP_ISSUE(SL, PL)                                                                              \
-  if (tid == 0) {                                                                                      \
-    const bool xin = FUSED && xpend && (PL) >= i_lo && (PL) < i_hi;                                    \
-    const unsigned mb = mbar0 + 8 * (SL);                                                              \
-    fence_proxy_async();                                                                               \
-    mbar_expect_tx(mb, (unsigned)((FUSED ? 2 : 1) * NF * SLOT * 8 + (xin ? NF * XSLOT * 8 : 0)));      \
-    if (FUSED) tma_load_4d(sr_base + (SL)*RS * 8, &tm_r, mb, k0 - 2, j0 - 1, (PL), 0);                 \
-    tma_load_4d(sp_base + (SL)*RS * 8, &tm_p, mb, k0 - 2, j0 - 1, (PL), 0);                            \
-    if (xin) tma_load_4d(sx_base + (SL)*NF * XSLOT * 8, &tm_x, mb, k0, j0, (PL), 0);                   \
-  }
 
     const double myo = s.mo[1], mzo = s.mo[2], kyo = s.ko[1], kzo = s.ko[2];
     const double mCor = myo * mzo, kCor = kyo * mzo + myo * kzo;
@@ -260,9 +269,6 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     }
 
     int ip = i_first;
-    __syncthreads();  // the ring is free: every thread finished the previous run
-    DPP_ISSUE(2, i_first)
-    if (i_first + 1 <= i_hi) DPP_ISSUE(0, i_first + 1)
 
   // one plane step: plane ip is in ring slot C; plane ip+2 is fetched into slot B (= slot of plane ip-1)
 #define DPP_STEP(A, B, C)                                                                             \
@@ -444,9 +450,9 @@ __global__ void __launch_bounds__(VT, 3) k_cg_r_update(const RArgs a) {
   __shared__ double tab[16];
   __shared__ int last_flag;
   pdl_launch_dependents();
+  if (threadIdx.x < 16) tab[threadIdx.x] = (threadIdx.x < 8 * a.nf) ? a.dtab[threadIdx.x] : 1.0;   // per-solve constant
   pdl_wait();
   if (!INIT && a.S[S_REASON] != 0.0) return;
-  if (threadIdx.x < 16) tab[threadIdx.x] = (threadIdx.x < 8 * a.nf) ? a.dtab[threadIdx.x] : 1.0;
   __syncthreads();
   const double alpha = INIT ? 0.0 : a.S[S_ALPHA];
   const long long nown = a.oe - a.ob;                                      // even (whole padded planes)
