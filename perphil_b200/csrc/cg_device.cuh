@@ -34,52 +34,67 @@ __device__ __forceinline__ double block_sum(double v, double* sm /*[VT/32]*/) {
   return t;
 }
 
-__device__ __forceinline__ void apply_post(double* S, double* hist, int post) {
-  // executed by one thread after the reduction values are in S[S_TMP..]
+// KSPCG bookkeeping after a reduction, executed by one thread.  t0, t1: the reduced values; S: the scalar slot
+// (written); R: where the slot's PREVIOUS state is read from -- the slot itself, or a shared-memory snapshot the
+// kernel took in its prologue (S changes only in these epilogues, stream-ordered, so the snapshot is current;
+// reading it saves two dependent L2 round trips on the critical path of every iteration).
+__device__ __forceinline__ void apply_post(double* S, double* hist, int post, const double* R, double t0, double t1) {
   if (post == POST_CG_PAP) {
-    if (S[S_REASON] != 0.0) return;  // the apply was a no-op: partials are stale
-    const double pap = S[S_TMP];
+    if (R[S_REASON] != 0.0) return;  // the apply was a no-op: partials are stale
+    const double pap = t0;
     S[S_PAP] = pap;
     if (!(pap > 0.0)) {
       S[S_REASON] = (pap == pap) ? DPP_DIVERGED_INDEFINITE_MAT : DPP_DIVERGED_NANORINF;
       S[S_XPEND] = 0.0;
     } else {
-      S[S_ALPHA] = S[S_RZ] / pap;
+      S[S_ALPHA] = R[S_RZ] / pap;
       S[S_XPEND] = 1.0;
     }
     return;
   }
   if (post == POST_CG_INIT || post == POST_CG_RZ) {
-    if (S[S_REASON] != 0.0) return;
-    const double rz = S[S_TMP], zz = S[S_TMP + 1];
+    if (R[S_REASON] != 0.0) return;
+    const double rz = t0, zz = t1;
     const double rnorm = sqrt(zz);
+    const double atol = R[S_ATOL];
+    double ttol = R[S_TTOL], rnorm0 = R[S_RNORM0];
     int its;
     if (post == POST_CG_INIT) {
       its = 0;
       S[S_RZ_OLD] = 1.0;
       S[S_RNORM0] = rnorm;
-      const double t = S[S_RTOL] * rnorm;
-      S[S_TTOL] = t > S[S_ATOL] ? t : S[S_ATOL];
+      rnorm0 = rnorm;
+      const double t = R[S_RTOL] * rnorm;
+      ttol = t > atol ? t : atol;
+      S[S_TTOL] = ttol;
     } else {
-      its = (int)S[S_ITS] + 1;
-      S[S_RZ_OLD] = S[S_RZ];
+      its = (int)R[S_ITS] + 1;
+      S[S_RZ_OLD] = R[S_RZ];
     }
     S[S_RZ] = rz;
     S[S_ZZ] = zz;
     S[S_RNORM] = rnorm;
     S[S_ITS] = (double)its;
-    if (hist != nullptr && its < (int)S[S_HISTCAP]) hist[its] = rnorm;
+    if (hist != nullptr && its < (int)R[S_HISTCAP]) hist[its] = rnorm;
     // KSPConvergedDefault
     double reason = 0.0;
     if (!(rnorm == rnorm) || isinf(rnorm)) reason = DPP_DIVERGED_NANORINF;
-    else if (rnorm <= S[S_TTOL]) reason = (rnorm < S[S_ATOL]) ? DPP_CONVERGED_ATOL : DPP_CONVERGED_RTOL;
-    else if (rnorm >= S[S_DTOL] * S[S_RNORM0]) reason = DPP_DIVERGED_DTOL;
+    else if (rnorm <= ttol) reason = (rnorm < atol) ? DPP_CONVERGED_ATOL : DPP_CONVERGED_RTOL;
+    else if (rnorm >= R[S_DTOL] * rnorm0) reason = DPP_DIVERGED_DTOL;
     else if (rz == 0.0) reason = DPP_CONVERGED_ATOL;
-    else if (its >= (int)S[S_MAXIT]) reason = DPP_DIVERGED_ITS;
+    else if (its >= (int)R[S_MAXIT]) reason = DPP_DIVERGED_ITS;
     S[S_REASON] = reason;
   }
 }
+__device__ __forceinline__ void apply_post(double* S, double* hist, int post) {
+  apply_post(S, hist, post, S, S[S_TMP], S[S_TMP + 1]);
+}
 
+constexpr int kPreScalars = 16;   // S[0 .. S_TMP): what a kernel prologue snapshots for its epilogue
+struct FoldPre {                  // shared-memory snapshot taken after griddepcontrol.wait (null members: read global)
+  const double* S;                // [kPreScalars]
+  const unsigned long long* seq;  // mailbox sequence counter
+};
 
 // Reduction epilogue run by ONE block of VT threads: S[S_TMP + out_offset + w] = sum over blocks (fixed
 // order) of partials[b*width + w], all-reduced over the ranks' mailboxes when ipc.world > 1, then the
@@ -100,7 +115,7 @@ __device__ __forceinline__ void apply_post(double* S, double* hist, int post) {
 // sm: kFinishSmem doubles of shared memory.
 __device__ __forceinline__ void finish_reduction(const double* __restrict__ partials, int nblocks, int width, double* S,
                                                  double* hist, int post, int out_offset, const IpcReduce& ipc,
-                                                 double* sm, bool sys_release = true) {
+                                                 double* sm, bool sys_release = true, FoldPre pre = FoldPre{nullptr, nullptr}) {
   double* vals = sm + VT / 32;
   volatile int* timed_out = reinterpret_cast<volatile int*>(sm + VT / 32 + kMboxEntry);
   double* recv = sm + VT / 32 + kMboxEntry + 2;   // [world][kMboxEntry - 1]
@@ -142,7 +157,11 @@ __device__ __forceinline__ void finish_reduction(const double* __restrict__ part
   }
   const bool dist = ipc.world > 1;
   unsigned long long* seq_sm = reinterpret_cast<unsigned long long*>(sm + VT / 32 + kMboxEntry + 1);
-  if (dist && tid == 0) *seq_sm = ++(*ipc.seq_dev);
+  if (dist && tid == 0) {
+    const unsigned long long sq = (pre.seq != nullptr ? *pre.seq : *ipc.seq_dev) + 1;
+    *ipc.seq_dev = sq;
+    *seq_sm = sq;
+  }
   __syncthreads();
   const unsigned long long seq = dist ? *seq_sm : 0ull;
   const int slot = (int)(seq & 1ull);
@@ -195,6 +214,7 @@ __device__ __forceinline__ void finish_reduction(const double* __restrict__ part
     if (*timed_out) {
       S[S_REASON] = (double)DPP_DIVERGED_COMM_TIMEOUT;
     } else {
+      double tw[2] = {0.0, 0.0};
       for (int w = 0; w < width; ++w) {
         double t = vals[w];
         if (dist) {
@@ -202,8 +222,10 @@ __device__ __forceinline__ void finish_reduction(const double* __restrict__ part
           for (int r = 0; r < ipc.world; ++r) t += recv[r * (kMboxEntry - 1) + w];
         }
         S[S_TMP + out_offset + w] = t;
+        if (w < 2) tw[w] = t;
       }
-      apply_post(S, hist, post);
+      if (out_offset == 0) apply_post(S, hist, post, pre.S != nullptr ? pre.S : S, tw[0], tw[1]);
+      else apply_post(S, hist, post);
     }
   }
 }

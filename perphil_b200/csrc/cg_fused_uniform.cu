@@ -108,6 +108,8 @@ struct __align__(128) Smem {
   double red[TY];
   double dtab[16];
   double fin[kFinishSmem];
+  double spre[kPreScalars];          // scalar slot as of the kernel start (epilogue reads it: cg_device.cuh)
+  unsigned long long seq_pre;
   int last_flag;
 };
 
@@ -140,6 +142,10 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
   if (tid < 16) sm.dtab[tid] = (FUSED && tid < 8 * NF) ? s.dtab[tid] : 1.0;
   pdl_wait();  // everything below reads what the previous kernel of the stream produced
   if (FUSED && s.S[S_REASON] != 0.0) return;
+  if (FUSED && s.fold.enabled) {
+    if (tid < kPreScalars) sm.spre[tid] = s.fold.S[tid];
+    if (tid == kPreScalars && s.fold.ipc.world > 1) sm.seq_pre = *s.fold.ipc.seq_dev;
+  }
   // scalars of the iteration (device resident; written by the reduction epilogues)
   double beta = 0.0, alpha_prev = 0.0;
   bool xpend = false;
@@ -382,7 +388,7 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     }
     if (FUSED && s.fold.enabled && last_block_arrives(s.fold.counter, gridDim.x, &sm.last_flag))
       finish_reduction(s.dot_partials, (int)gridDim.x, 1, s.fold.S, s.fold.hist, s.fold.post, 0, s.fold.ipc, sm.fin,
-                       s.fold.ipc.ll == 3);
+                       s.fold.ipc.ll == 3, FoldPre{sm.spre, &sm.seq_pre});
   }
 }
 
@@ -448,11 +454,17 @@ template <bool INIT>
 __global__ void __launch_bounds__(VT, 3) k_cg_r_update(const RArgs a) {
   __shared__ double sm[kFinishSmem];
   __shared__ double tab[16];
+  __shared__ double spre[kPreScalars];
+  __shared__ unsigned long long seq_pre;
   __shared__ int last_flag;
   pdl_launch_dependents();
   if (threadIdx.x < 16) tab[threadIdx.x] = (threadIdx.x < 8 * a.nf) ? a.dtab[threadIdx.x] : 1.0;   // per-solve constant
   pdl_wait();
   if (!INIT && a.S[S_REASON] != 0.0) return;
+  if (a.fold.enabled) {   // snapshot for the epilogue (cg_device.cuh: apply_post / finish_reduction)
+    if (threadIdx.x < kPreScalars) spre[threadIdx.x] = a.fold.S[threadIdx.x];
+    if (threadIdx.x == kPreScalars && a.fold.ipc.world > 1) seq_pre = *a.fold.ipc.seq_dev;
+  }
   __syncthreads();
   const double alpha = INIT ? 0.0 : a.S[S_ALPHA];
   const long long nown = a.oe - a.ob;                                      // even (whole padded planes)
@@ -539,7 +551,7 @@ __global__ void __launch_bounds__(VT, 3) k_cg_r_update(const RArgs a) {
   if (remote && a.halo.debug_fence_all) __threadfence_system();
   if (a.fold.enabled && last_block_arrives(a.fold.counter, gridDim.x * gridDim.y, &last_flag))
     finish_reduction(a.partials, (int)(gridDim.x * gridDim.y), 2, a.fold.S, a.fold.hist, a.fold.post, 0, a.fold.ipc, sm,
-                     remote || INIT);
+                     remote || INIT, FoldPre{spre, &seq_pre});
 }
 
 // boundary planes of r -> the neighbours' ghost planes (start of a solve)
