@@ -7,6 +7,8 @@
 #include <nccl.h>  // types only: the library is bound at run time (see NcclApi)
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -193,7 +195,19 @@ int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n) {
 bool comm_ipc_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc; }
 bool comm_ipc_halo_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc && ctx->comm->ipc_halo; }
 
+// Measurement switches that deliberately break the protocol (profiles/r01_exchange_cost.md): never silent.
+static void warn_measurement_switches() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* ll = getenv("DPP_MBOX_LL");
+  if (getenv("DPP_DEBUG_NO_MBOX") || getenv("DPP_DEBUG_NO_PUSH") || (ll != nullptr && atoi(ll) == 2))
+    fprintf(stderr, "libdppb200: DPP_DEBUG_NO_MBOX / DPP_DEBUG_NO_PUSH / DPP_MBOX_LL=2 are timing experiments: "
+                    "the multi-GPU RESULTS OF THIS RUN ARE INVALID\n");
+}
+
 IpcReduce comm_ipc_reduce_args(dpp_context* ctx) {
+  warn_measurement_switches();
   Comm* C = ctx->comm;
   IpcReduce a{};
   a.world = 1;
