@@ -351,10 +351,13 @@ def h_apply_structured(h, x):
     return y
 
 
-def test_solve_128_residual_and_convergence():
-    """Full-size property: the returned solution satisfies the lifted system to the requested rtol
-    (checked with an independent apply), and the iteration count follows the O(N) growth 10/15/31/46."""
-    N = 128
+@pytest.mark.parametrize("N,its_range", [(128, (219, 219)), (256, (380, 395))])
+def test_solve_full_size_residual_and_convergence(N, its_range):
+    """Full-size property (BASELINE configs[2] is N = 256): the returned solution satisfies the lifted system to
+    the requested rtol, checked with an INDEPENDENT apply (the LDGSTS kernel in the caller's layout; the solve
+    ran on the TMA kernels in the padded layout), the boundary values are exactly g, and the iteration count is
+    the one the C/OpenMP oracle takes at 128^3 (219: bench.py's cpu_baseline leg) / continues its O(N) growth at
+    256^3 (387 in every bench run)."""
     mesh = pb.UnitCubeMesh(N, N, N)
     _, V = pb.create_function_spaces(mesh)
     W = V * V
@@ -363,7 +366,7 @@ def test_solve_128_residual_and_convergence():
     bcs = [pb.DirichletBC(W.sub(0), p1, "on_boundary"), pb.DirichletBC(W.sub(1), p2, "on_boundary")]
     sol = pb.solve_dpp(W, prm, bcs, solver_parameters={**pb.B200_CG_JACOBI_PARAMS, "b200_history": 2048})
     info = pb.last_solve_info()
-    assert info.converged_reason > 0 and 150 < sol.iteration_number < 400
+    assert info.converged_reason > 0 and its_range[0] <= sol.iteration_number <= its_range[1]
     assert len(info.history) == sol.iteration_number + 1
     h = pb.handle_for(W)
     n = h.n_nodes
