@@ -235,6 +235,10 @@ int dpp_time_apply(dpp_handle h, int operator_mode, int warmup, int reps, int wi
  * Returns DPP_ERR_INVALID when the handle does not run the fused path. */
 int dpp_time_cg_kernels(dpp_handle h, int warmup, int reps, double* apply_ms, double* update_ms, double* matvec_ms);
 int dpp_kernel_launch_count(dpp_handle h, int64_t* launches); /* kernels launched so far by this handle */
+/* The launch plan of the plane-streaming apply kernels: number of x-segments chosen for `tiles` in-plane tiles,
+ * `planes` owned x-planes, `resident_ctas` co-resident CTAs (2 per SM) and at most `max_ctas` CTAs (host-only,
+ * no GPU needed; the cost model and the measurements behind it: DESIGN.md 4.2, csrc/dpp_internal.cuh). */
+int dpp_plan_x_segments(int tiles, int planes, int resident_ctas, int max_ctas);
 
 #ifdef __cplusplus
 }

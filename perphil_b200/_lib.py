@@ -81,6 +81,7 @@ _PROTOTYPES = {
     "dpp_time_cg_kernels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double)]),
     "dpp_kernel_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "dpp_plan_x_segments": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dpp_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "dpp_error_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dpp_darcy_velocity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int32, C.c_void_p,

@@ -587,6 +587,11 @@ int dpp_host_alloc(void** ptr, int64_t bytes) {
 
 int dpp_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? DPP_OK : DPP_ERR_CUDA; }
 
+int dpp_plan_x_segments(int tiles, int planes, int resident_ctas, int max_ctas) {
+  if (tiles < 1 || planes < 1 || resident_ctas < 1 || max_ctas < tiles) return DPP_ERR_INVALID;
+  return dpp::choose_x_segments(tiles, planes, resident_ctas, max_ctas);
+}
+
 int dpp_kernel_launch_count(dpp_handle ctx, int64_t* launches) {
   if (!ctx || !launches) return DPP_ERR_INVALID;
   *launches = ctx->launches;

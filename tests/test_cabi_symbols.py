@@ -92,3 +92,23 @@ def test_product_package_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert "dpp_oracle" not in txt, f
+
+
+def test_x_segment_plan_matches_the_measured_optima():
+    """Host-only launch planning of the plane-streaming kernels (csrc/dpp_internal.cuh: choose_x_segments): the
+    segment counts that tools/sched_sweep.py measured fastest on a B200 (296 resident CTAs, 128 interior tiles of
+    a 257^2 plane): 33-plane slab -> 2 (48.5 us; 1: 64, 3: 57, 4: 51.5), 128 layers -> 4 (159.5 us; 2: 164.9,
+    9: 165.7), 256 layers -> 9 (303 us; 2 segments of 128 planes: 327, 7: 335, 11: 302, 13: 307)."""
+    from perphil_b200 import _lib as L
+
+    lib = L.load()
+    plan = lambda planes: lib.dpp_plan_x_segments(128, planes, 296, 4096)
+    assert plan(31) == 2
+    assert plan(127) == 4
+    assert plan(255) == 9
+    assert lib.dpp_plan_x_segments(128, 1, 296, 4096) == 1
+    assert lib.dpp_plan_x_segments(0, 31, 296, 4096) < 0   # DPP_ERR_INVALID
+    # never more CTAs than allowed, never a run shorter than 4 planes (unless a single segment)
+    for tiles, planes in ((153, 257), (16, 500), (2000, 64), (8, 9)):
+        n = lib.dpp_plan_x_segments(tiles, planes, 296, 4096)
+        assert n >= 1 and (n == 1 or (tiles * n <= 4096 and -(-planes // n) >= 4))
