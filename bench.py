@@ -90,11 +90,35 @@ def build_problem(N, comm=None):
     return W, V, prm, bcs
 
 
-def cpu_baseline(N, repeats=1):
+def host_threads():
+    """Threads the CPU legs use: every core this process may run on -- set explicitly, because launchers
+    (torch.distributed.run) export OMP_NUM_THREADS=1 and would otherwise silently change the baseline."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_baseline(N, repeats=1, single_thread_size=64):
     """C/OpenMP restatement of the reference's CPU path (assembled AIJ + SeqAIJ MatMult + KSPCG/PCJACOBI,
-    oracle/dpp_oracle_c.c) on a bounded sample of the workload, all host threads."""
+    oracle/dpp_oracle_c.c) on a bounded sample of the workload: all host threads, plus the reference's own
+    protocol -- one thread (notebooks/petsc-profiling-time-benchmarks-3d.py:11 runs OMP_NUM_THREADS=1) -- on a
+    smaller sample so the default bench run stays within minutes."""
     from oracle import c_oracle as co
 
+    nthr = host_threads()
+    co.set_num_threads(nthr)
     t0 = time.perf_counter()
     csys = co.manufactured_system((N, N, N), 1)
     t_asm = time.perf_counter() - t0
@@ -106,12 +130,26 @@ def cpu_baseline(N, repeats=1):
         best = dt if best is None else min(best, dt)
     ndof, nnz = csys.n_dof, csys.nnz
     csys.close()
-    return {"value": ndof * res.iteration_number / best / 1e9, "unit": "GDoF/s", "cores": co.num_threads(),
+    one = None
+    if single_thread_size:
+        M = single_thread_size
+        c1 = co.manufactured_system((M, M, M), 1)
+        co.set_num_threads(1)
+        t0 = time.perf_counter()
+        r1 = c1.cg("jacobi", want_solution=False)
+        d1 = time.perf_counter() - t0
+        co.set_num_threads(nthr)
+        one = {"value": c1.n_dof * r1.iteration_number / d1 / 1e9, "unit": "GDoF/s", "cores": 1,
+               "sample": f"{M}^3 hex Q1 ({c1.n_dof} DoF), {r1.iteration_number} its in {d1:.2f} s, OMP threads 1 "
+                         "(the reference's profiling protocol)"}
+        c1.close()
+    return {"value": ndof * res.iteration_number / best / 1e9, "unit": "GDoF/s", "cores": nthr,
             "kind": "port",
             "sample": f"{N}^3 hex Q1 ({ndof} DoF, nnz {nnz}), C/OpenMP CSR SpMV + Jacobi-CG (PETSc KSPCG semantics), "
                       f"{res.iteration_number} its in {best:.2f} s (assembly {t_asm:.1f} s not included; "
                       f"SpMV {100 * res.spmv_seconds / best:.0f}% of the solve)",
-            "iterations": int(res.iteration_number), "seconds": best, "host_cpus": os.cpu_count()}
+            "iterations": int(res.iteration_number), "seconds": best, "host_cpus": os.cpu_count(),
+            "cpu_model": cpu_model(), "single_thread": one}
 
 
 def run_reference(args):
@@ -123,7 +161,9 @@ def run_reference(args):
         return
     from oracle import c_oracle as co
 
-    N = args.ref_size
+    N = args.cpu_size
+    nthr = host_threads()
+    co.set_num_threads(nthr)   # identical at every N: the launcher's OMP_NUM_THREADS does not decide the baseline
     csys = co.manufactured_system((N, N, N), 1)
     res = None
     for _ in range(args.warmup):
@@ -134,7 +174,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     val = csys.n_dof * res.iteration_number / dt / 1e9
     sample = (f"{N}^3 hex Q1 ({csys.n_dof} DoF), assembled CSR SpMV + Jacobi-CG, {res.iteration_number} its per step, "
-              f"{co.num_threads()} OpenMP threads")
+              f"{co.num_threads()} OpenMP threads on {cpu_model()}")
     line = {
         "impl": "reference", "metric": "dpp_solve_gdofs", "value": val, "unit": "GDoF/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -154,8 +194,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--size", type=int, default=256, help="cells per direction (BASELINE configs[2]: 256)")
-    ap.add_argument("--ref-size", type=int, default=96)
-    ap.add_argument("--cpu-size", type=int, default=128)
+    ap.add_argument("--cpu-size", type=int, default=96,
+                    help="cells per direction of the bounded CPU sample (cpu_baseline AND --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -177,14 +217,20 @@ def main():
     torch.cuda.set_device(local_rank)
     N = args.size
     W, V, prm, bcs = build_problem(N, comm)
-    h = pb.handle_for(W)
+    t0 = time.perf_counter()
+    h = pb.handle_for(W)          # dpp_create: mesh upload, structured detection, (N > 1) NCCL + IPC wiring
+    create_ms = (time.perf_counter() - t0) * 1e3
     info = h.info()
     n_nodes_global = (N + 1) ** 3
     ndof = 2 * n_nodes_global
     preset = pb.B200_CG_JACOBI_PARAMS
 
-    # ---- e2e warm-up through the public API (also uploads BCs / params)
-    for _ in range(max(args.warmup, 3)):
+    # ---- e2e warm-up through the public API (also uploads BCs / params); the very first call carries the
+    # one-time costs (BC upload + classification, work-vector allocation, tensor maps, CUDA-graph capture)
+    t0 = time.perf_counter()
+    sol = pb.solve_dpp(W, prm, bcs, solver_parameters=preset)
+    first_solve_ms = (time.perf_counter() - t0) * 1e3
+    for _ in range(max(args.warmup, 3) - 1):
         sol = pb.solve_dpp(W, prm, bcs, solver_parameters=preset)
     its = sol.iteration_number
     opt = options_from_petsc(h, preset)
@@ -255,6 +301,8 @@ def main():
         dom_bytes, dom_ms = apply_bytes, apply_ms
         iter_bytes = apply_bytes + 88 * ndof      # unfused-kernel minimum
         bytes_model = "58 B/node + 32 B/cell"
+    # per-rank figures: at N > 1 every rank launches the kernel on its slab (1/N of the DoF); the time is the max
+    # over ranks, so bytes / world / time is what ONE GPU achieves against ITS HBM peak
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 / world
     solve_gbs = iter_bytes * its / (np.mean([m for m in dev_ms]) * 1e-3) / 1e9 / world
 
@@ -277,10 +325,17 @@ def main():
         "e2e": {"value": ndof * its / (e2e_ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
+        "first_call_ms": {"dpp_create": create_ms, "first_solve_dpp": first_solve_ms,
+                          "note": "one-time costs outside every other number: mesh upload + structured detection; "
+                                  "first solve = BC upload/classification, work vectors, tensor maps, graph capture"},
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": TRAFFIC_NCU.get("fused_apply") if fused else None,
-                     "peak_kind": peak_kind, "bytes_model": bytes_model, "algorithmic_bytes": dom_bytes,
+                     "frac": achieved / peak,
+                     # ncu dram bytes of ONE launch: captured on one GPU at 256^3 only (profiles/); no capture
+                     # exists for the per-rank slab kernels, so N > 1 and other sizes report null
+                     "traffic": TRAFFIC_NCU.get("fused_apply") if (fused and world == 1 and N == 256) else None,
+                     "peak_kind": peak_kind, "bytes_model": bytes_model,
+                     "algorithmic_bytes": dom_bytes // world, "algorithmic_bytes_scope": "per rank, per launch",
                      "ms_per_launch": dom_ms},
         "kernels": {"cg_fused_apply_ms": fa_ms, "cg_r_update_ms": fu_ms, "tma_matvec_ms": mv_ms, "plain_apply_ms": apply_ms,
                     "plain_apply_gbs": apply_bytes / (apply_ms * 1e-3) / 1e9 / world,

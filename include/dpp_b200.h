@@ -161,6 +161,13 @@ int dpp_comm_ipc_import(dpp_handle h, const void* blobs_all_ranks);
  * dpp_info.peer_memory must agree across ranks; bit 0 = mailbox all-reduce, bit 1 = halo push) */
 int dpp_comm_ipc_disable(dpp_handle h);
 
+/* Slab runs: whether the fused two-kernel Jacobi-CG iteration (uniform tensor grid, TMA available) serves this
+ * handle is a rank-local fact, but the number and kind of reductions per iteration depends on it, so all ranks must
+ * run the same protocol.  The host layer all-gathers dpp_fused_cg_supported() (1 / 0) and, when the ranks disagree,
+ * calls dpp_set_fused_cg(h, 0) on every rank (the unfused kernel sequence then runs everywhere). */
+int dpp_fused_cg_supported(dpp_handle h);
+int dpp_set_fused_cg(dpp_handle h, int enable);
+
 /* ---- operator ------------------------------------------------------------------------------- */
 
 /* y = A_bc x with A_bc = P A P + (I - P) (Firedrake DirichletBC semantics), A the dpp_form matrix
@@ -178,6 +185,14 @@ int dpp_get_diagonal_host(dpp_handle h, double* diag_host);
 int dpp_assemble_csr(dpp_handle h, int64_t* nnz);
 /* petsc_matrix.getValuesCSR() (conditioning.py:85): indptr [2*n_nodes+1], indices/data [nnz] */
 int dpp_get_csr_host(dpp_handle h, int64_t* indptr_host, int32_t* indices_host, double* data_host);
+
+/* One block of that matrix as a scalar-space CSR matrix (row field, column field in {0, 1}): what
+ * get_matrix_data_from_form(a_macro, [bc]) / (a_micro, [bc]) of the dpp_delayed_form split (forms/dpp.py:135-205,
+ * used at notebooks/conforming-galerkin-fem-operator-splitting-2D-perphil.py:463-480) returns, and the slices
+ * csr[:n0, :n0] / csr[n0:, n0:] of iterative_bench.py:323-324, gathered on the device.
+ * indptr [n_nodes+1], indices / data [nnz / 4]; call dpp_assemble_csr first. */
+int dpp_get_csr_block_host(dpp_handle h, int row_field, int col_field, int64_t* indptr_host, int32_t* indices_host,
+                           double* data_host);
 
 /* ---- solve: LinearVariationalSolver.solve() + ksp getters (solver.py:66-74) ------------------ */
 
@@ -234,6 +249,10 @@ int dpp_time_apply(dpp_handle h, int operator_mode, int warmup, int reps, int wi
  * matvec_ms = the same TMA kernel in plain mode (w = A p, fused <p,Ap>: PETSc MatMult on the path).
  * Returns DPP_ERR_INVALID when the handle does not run the fused path. */
 int dpp_time_cg_kernels(dpp_handle h, int warmup, int reps, double* apply_ms, double* update_ms, double* matvec_ms);
+/* device milliseconds of the two assembly phases: symbolic (node graph, row pointers, scatter permutation,
+ * block pattern; rebuilt from scratch) and numeric (mean of `reps` value fills through the permutation; the
+ * bandwidth model is 12 B per stored entry: 8 B value written + 4 B column index of the pattern). */
+int dpp_time_assembly(dpp_handle h, int reps, double* symbolic_ms, double* numeric_ms, int64_t* nnz);
 int dpp_kernel_launch_count(dpp_handle h, int64_t* launches); /* kernels launched so far by this handle */
 /* The launch plan of the plane-streaming apply kernels: number of x-segments chosen for `tiles` in-plane tiles,
  * `planes` owned x-planes, `resident_ctas` co-resident CTAs (2 per SM) and at most `max_ctas` CTAs (host-only,

@@ -41,6 +41,11 @@ def load(build: bool = True):
     lib.orc_cg.restype = C.c_int
     lib.orc_cg.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p,
                            C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    lib.orc_gmres.restype = C.c_int
+    lib.orc_gmres.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                              C.c_double, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                              C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+    lib.orc_get_b.argtypes = [C.c_void_p, C.c_void_p]
     lib.orc_num_threads.restype = C.c_int
     lib.orc_set_num_threads.argtypes = [C.c_int]
     _LIB = lib
@@ -116,6 +121,41 @@ class COracleSystem:
         return CgResult(u, int(its), float(rn.value), int(reason.value), list(hist[:min(history, its + 1)]),
                         float(tmv.value))
 
+    def rhs(self) -> np.ndarray:
+        """Lifted right-hand side b = -(A u0) on unconstrained rows (solver.py:66-71)."""
+        b = np.empty(self.n_dof)
+        self._lib.orc_get_b(self._h, _ptr(b))
+        return b
+
+    def gmres(self, pc: str = "none", restart=30, rtol=1e-8, atol=1e-12, dtol=1e4, max_it=50000, inner=None,
+              want_solution=True, history=0) -> "GmresResult":
+        """KSPGMRES(restart), left PC: 'none' | 'jacobi' | 'fieldsplit' (multiplicative) | 'fieldsplit_additive';
+        ``inner`` = dict(ksp_type='cg'|'preonly', ksp_rtol, ksp_atol, ksp_max_it) for the Jacobi-CG block solves."""
+        code = {"none": 0, "jacobi": 1, "fieldsplit": 2, "fieldsplit_additive": 3}[pc]
+        inner = inner or {}
+        u = np.empty(self.n_dof) if want_solution else None
+        hist = np.zeros(max(history, 1))
+        rn, reason, inner_its = C.c_double(), C.c_int(), C.c_int64()
+        its = self._lib.orc_gmres(self._h, code, restart, rtol, atol, dtol, max_it,
+                                  0 if inner.get("ksp_type", "cg") == "preonly" else 1,
+                                  inner.get("ksp_rtol", 1e-5), inner.get("ksp_atol", 1e-50),
+                                  inner.get("ksp_max_it", 10000), _ptr(u), C.byref(rn), C.byref(reason),
+                                  _ptr(hist) if history else None, history, C.byref(inner_its))
+        h = hist[:history] if history else hist[:0]
+        nz = np.flatnonzero(h)   # entries written (every recorded norm is > 0 except an exact-zero final one)
+        return GmresResult(u, int(its), float(rn.value), int(reason.value), list(h[:nz[-1] + 1] if nz.size else h[:0]),
+                           int(inner_its.value))
+
+
+@dataclass
+class GmresResult:
+    u: Optional[np.ndarray]
+    iteration_number: int
+    residual_error: float
+    reason: int
+    history: List[float]
+    inner_iterations: int
+
 
 def num_threads() -> int:
     return int(load().orc_num_threads())
@@ -123,6 +163,26 @@ def num_threads() -> int:
 
 def set_num_threads(n: int):
     load().orc_set_num_threads(int(n))
+
+
+def _boundary_nodes(cells: Sequence[int], degree: int):
+    cells = tuple(int(c) for c in cells)
+    counts = [degree * c + 1 for c in cells]
+    on_b = np.zeros(counts, dtype=bool)
+    for d, c in enumerate(counts):
+        sl = [slice(None)] * len(counts)
+        for edge in (0, c - 1):
+            sl[d] = edge
+            on_b[tuple(sl)] = True
+    return np.flatnonzero(on_b.ravel()).astype(np.int32)
+
+
+def constant_bc_system(cells: Sequence[int], degree: int = 1, k1=1.0, k2=1e-6, beta=1e2, mu=1.0, p1=1.0,
+                       p2=0.0) -> COracleSystem:
+    """BASELINE config 5 data: constants p1, p2 on the whole boundary (petsc_profiling.py:685-690)."""
+    nb = _boundary_nodes(cells, degree)
+    return COracleSystem(cells, degree, k1, k2, beta, mu, nb, np.full(nb.size, float(p1)), nb,
+                         np.full(nb.size, float(p2)))
 
 
 def manufactured_system(cells: Sequence[int], degree: int = 1, k1=1.0, k2=1e-2, beta=1.0, mu=1.0) -> COracleSystem:

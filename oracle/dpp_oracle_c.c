@@ -268,6 +268,217 @@ int orc_cg(const orc_system* s, int pc, double rtol, double atol, double dtol, i
   return its;
 }
 
+void orc_get_b(const orc_system* s, double* b) { memcpy(b, s->b, sizeof(double) * (size_t)s->n_dof); }
+
+/* ------------------------------------------------------------------------------------------------
+ * KSPGMRES(restart) with left preconditioning and PCFIELDSPLIT (solvers/parameters.py:21-57;
+ * BASELINE config 5).  Same arithmetic as oracle/dpp_oracle.py: ksp_gmres / pc_fieldsplit, to which
+ * tests/test_oracle_c.py pins it: classical Gram-Schmidt without refinement (VecMDot on the
+ * un-modified w, then VecMAXPY), Givens residual recurrence, true preconditioned residual
+ * recomputed at each restart, zero initial guess, KSPConvergedDefault on the preconditioned norm.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* y = A[fr][fc] x on one field block; every row stores its field-0 columns first, then field 1 */
+static void spmv_block(const orc_system* s, int fr, int fc, const double* x, double* y) {
+  const int64_t nn = s->n_nodes;
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < nn; ++r) {
+    const int64_t row = (int64_t)fr * nn + r;
+    const int64_t q0 = s->indptr[row], half = (s->indptr[row + 1] - q0) / 2;
+    const int64_t qa = q0 + (fc ? half : 0);
+    double acc = 0.0;
+    for (int64_t q = qa; q < qa + half; ++q) acc += s->data[q] * x[s->indices[q] - (int64_t)fc * nn];
+    y[r] = acc;
+  }
+}
+
+typedef struct {
+  int ksp;         /* 0 = preonly (one Jacobi application), 1 = cg */
+  double rtol, atol;
+  int max_it;
+} orc_inner;
+
+/* inner block solve  y = A_ff^-1 r  by Jacobi-CG (KSPCG semantics as orc_cg), zero initial guess */
+static int block_cg(const orc_system* s, int f, const orc_inner* in, const double* rhs, double* x, double* wk /*[4*nn]*/) {
+  const int64_t nn = s->n_nodes;
+  const double* diag = s->diag + (int64_t)f * nn;
+  double *r = wk, *z = wk + nn, *pv = wk + 2 * nn, *wv = wk + 3 * nn;
+  if (in->ksp == 0) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nn; ++i) x[i] = rhs[i] / diag[i];
+    return 1;
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nn; ++i) { x[i] = 0.0; r[i] = rhs[i]; z[i] = (1.0 / diag[i]) * r[i]; pv[i] = 0.0; }
+  double dp = sqrt(dot(nn, z, z)), rnorm0 = 0, ttol = 0;
+  int reason = conv_test(0, dp, &rnorm0, &ttol, in->rtol, in->atol, 1e4);
+  double beta = dot(nn, z, r), betaold = 1.0;
+  int its = 0;
+  while (!reason) {
+    if (its >= in->max_it || beta == 0.0) break;
+    const double bb = its == 0 ? 0.0 : beta / betaold;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nn; ++i) pv[i] = z[i] + bb * pv[i];
+    betaold = beta;
+    spmv_block(s, f, f, pv, wv);
+    const double dpi = dot(nn, pv, wv);
+    if (!(dpi > 0.0) || !isfinite(dpi)) break;
+    const double a = beta / dpi;
+    double zz = 0.0, rz = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : zz, rz)
+    for (int64_t i = 0; i < nn; ++i) {
+      x[i] += a * pv[i];
+      const double rn = r[i] - a * wv[i];
+      r[i] = rn;
+      const double zv = (1.0 / diag[i]) * rn;
+      z[i] = zv;
+      zz += zv * zv;
+      rz += zv * rn;
+    }
+    dp = sqrt(zz);
+    beta = rz;
+    ++its;
+    reason = conv_test(its, dp, &rnorm0, &ttol, in->rtol, in->atol, 1e4);
+  }
+  return its;
+}
+
+/* pc: 0 none, 1 jacobi, 2 fieldsplit multiplicative, 3 fieldsplit additive.  out = B in */
+static void pc_apply(const orc_system* s, int pc, const orc_inner* in, const double* vin, double* vout, double* wk,
+                     int64_t* inner_its) {
+  const int64_t n = s->n_dof, nn = s->n_nodes;
+  if (pc == 0) { memcpy(vout, vin, sizeof(double) * (size_t)n); return; }
+  if (pc == 1) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) vout[i] = (1.0 / s->diag[i]) * vin[i];
+    return;
+  }
+  double* r1 = wk + 4 * nn;
+  *inner_its += block_cg(s, 0, in, vin, vout, wk);
+  if (pc == 2) {
+    spmv_block(s, 1, 0, vout, r1);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nn; ++i) r1[i] = vin[nn + i] - r1[i];
+  } else {
+    memcpy(r1, vin + nn, sizeof(double) * (size_t)nn);
+  }
+  *inner_its += block_cg(s, 1, in, r1, vout + nn, wk);
+}
+
+int orc_gmres(const orc_system* s, int pc, int restart, double rtol, double atol, double dtol, int max_it,
+              int inner_ksp, double inner_rtol, double inner_atol, int inner_max_it, double* u, double* rnorm_out,
+              int* reason_out, double* hist, int hist_cap, int64_t* inner_its_out) {
+  const int64_t n = s->n_dof;
+  const int m = restart;
+  orc_inner in = {inner_ksp, inner_rtol, inner_atol, inner_max_it};
+  double* x = (double*)calloc((size_t)n, sizeof(double));
+  double* V = (double*)malloc(sizeof(double) * (size_t)n * (size_t)(m + 1));
+  double* w = (double*)malloc(sizeof(double) * (size_t)n);
+  double* t = (double*)malloc(sizeof(double) * (size_t)n);
+  double* wk = (double*)malloc(sizeof(double) * (size_t)(5 * s->n_nodes));
+  double* H = (double*)calloc((size_t)(m + 2) * (size_t)(m + 1), sizeof(double));
+  double* cc = (double*)calloc((size_t)m + 1, sizeof(double));
+  double* ss = (double*)calloc((size_t)m + 1, sizeof(double));
+  double* grs = (double*)calloc((size_t)m + 2, sizeof(double));
+  double* hcol = (double*)calloc((size_t)m + 2, sizeof(double));
+#define HH(a, b) H[(size_t)(a) * (size_t)(m + 1) + (size_t)(b)]
+  int64_t inner_its = 0;
+  int its = 0, reason = 0, first = 1, nh = 0;
+  double res = 0.0, rnorm0 = 0, ttol = 0;
+  for (;;) {
+    if (first) {
+      pc_apply(s, pc, &in, s->b, w, wk, &inner_its);
+    } else {
+      orc_spmv(s, x, t);
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < n; ++i) t[i] = s->b[i] - t[i];
+      pc_apply(s, pc, &in, t, w, wk, &inner_its);
+    }
+    first = 0;
+    res = sqrt(dot(n, w, w));
+    if (hist && nh < hist_cap) hist[nh] = res;
+    ++nh;
+    if (res == 0.0) { reason = 3; break; }
+    reason = conv_test(its, res, &rnorm0, &ttol, rtol, atol, dtol);
+    if (reason) break;
+    if (its >= max_it) { reason = -3; break; }
+    memset(H, 0, sizeof(double) * (size_t)(m + 2) * (size_t)(m + 1));
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) V[i] = w[i] / res;
+    grs[0] = res;
+    int it = 0;
+    while (!reason && it < m && its < max_it) {
+      if (it) { if (hist && nh < hist_cap) hist[nh] = res; ++nh; }
+      orc_spmv(s, V + (size_t)it * n, t);
+      pc_apply(s, pc, &in, t, w, wk, &inner_its);
+      for (int j = 0; j <= it; ++j) hcol[j] = dot(n, V + (size_t)j * n, w);   /* VecMDot */
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < n; ++i) {                                        /* VecMAXPY */
+        double acc = w[i];
+        for (int j = 0; j <= it; ++j) acc -= hcol[j] * V[(size_t)j * n + i];
+        w[i] = acc;
+      }
+      const double tt = sqrt(dot(n, w, w));
+      int hapend = 0;
+      double hapbnd = 1e-30;
+      if (grs[it] != 0.0) { hapbnd = fabs(tt / grs[it]); if (hapbnd > 1e-30) hapbnd = 1e-30; }
+      if (tt < hapbnd) hapend = 1;
+      else {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) V[(size_t)(it + 1) * n + i] = w[i] / tt;
+      }
+      for (int j = 0; j <= it; ++j) HH(j, it) = hcol[j];
+      HH(it + 1, it) = tt;
+      for (int j = 0; j < it; ++j) {
+        const double a = HH(j, it);
+        HH(j, it) = cc[j] * a + ss[j] * HH(j + 1, it);
+        HH(j + 1, it) = cc[j] * HH(j + 1, it) - ss[j] * a;
+      }
+      if (!hapend) {
+        const double d = sqrt(HH(it, it) * HH(it, it) + HH(it + 1, it) * HH(it + 1, it));
+        if (d == 0.0) { reason = -5; break; }
+        cc[it] = HH(it, it) / d;
+        ss[it] = HH(it + 1, it) / d;
+        grs[it + 1] = -ss[it] * grs[it];
+        grs[it] = cc[it] * grs[it];
+        HH(it, it) = cc[it] * HH(it, it) + ss[it] * HH(it + 1, it);
+        res = fabs(grs[it + 1]);
+      } else {
+        res = 0.0;
+      }
+      ++it;
+      ++its;
+      reason = conv_test(its, res, &rnorm0, &ttol, rtol, atol, dtol);
+      if (hapend && !reason) reason = -5;
+    }
+    if (it && (reason || its >= max_it)) { if (hist && nh < hist_cap) hist[nh] = res; ++nh; }
+    if (it) {   /* KSPGMRESBuildSoln */
+      double* y = hcol;
+      for (int k = it - 1; k >= 0; --k) {
+        double acc = grs[k];
+        for (int j = k + 1; j < it; ++j) acc -= HH(k, j) * y[j];
+        y[k] = acc / HH(k, k);
+      }
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < n; ++i) {
+        double acc = x[i];
+        for (int j = 0; j < it; ++j) acc += y[j] * V[(size_t)j * n + i];
+        x[i] = acc;
+      }
+    }
+    if (reason) break;
+    if (its >= max_it) { reason = -3; break; }
+  }
+#undef HH
+  if (u)
+    for (int64_t i = 0; i < n; ++i) u[i] = s->u0[i] + x[i];
+  if (rnorm_out) *rnorm_out = res;
+  if (reason_out) *reason_out = reason;
+  if (inner_its_out) *inner_its_out = inner_its;
+  free(x); free(V); free(w); free(t); free(wk); free(H); free(cc); free(ss); free(grs); free(hcol);
+  return its;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -21,6 +21,6 @@ from .parameters import (B200_BACKEND, B200_BACKEND_KEY, B200_CG_FIELDSPLIT_PARA
                          B200_GMRES_PARAMS, B200_PICARD_SPLIT_PARAMS, DPPParameters)
 from .postprocessing import (VectorFunction, calculate_darcy_velocity_from_pressure, h1_seminorm_error, l2_error,
                              slice_along_x, split_dpp_solution)
-from .solver import Solution, handle_for, last_solve_info, release_handles, solve_dpp, solve_dpp_nonlinear
+from .solver import ConvergenceError, Solution, handle_for, last_solve_info, release_handles, solve_dpp, solve_dpp_nonlinear
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -68,11 +68,16 @@ _PROTOTYPES = {
     "dpp_comm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dpp_comm_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dpp_comm_ipc_disable": (C.c_int, [C.c_void_p]),
+    "dpp_fused_cg_supported": (C.c_int, [C.c_void_p]),
+    "dpp_set_fused_cg": (C.c_int, [C.c_void_p, C.c_int]),
     "dpp_apply_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dpp_apply_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "dpp_get_diagonal_host": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dpp_assemble_csr": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "dpp_get_csr_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dpp_get_csr_block_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dpp_time_assembly": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_int64)]),
     "dpp_default_options": (None, [C.POINTER(DppOptions)]),
     "dpp_solve": (C.c_int, [C.c_void_p, C.POINTER(DppOptions), C.c_void_p, C.POINTER(DppResult), C.c_void_p,
                             C.c_int32]),

@@ -52,6 +52,7 @@ class DppHandle:
             self._h = C.c_void_p()
             raise DppError(f"dpp_create failed ({rc}): {msg}")
         self._perm = None   # user -> internal node map (set_numbering)
+        self._uploaded = {}  # host copies of what set_params / set_dirichlet last sent (skip identical uploads)
 
     @classmethod
     def from_mesh_arrays(cls, dim: int, degree: int, cell_node_map: np.ndarray, node_coords: np.ndarray,
@@ -104,15 +105,26 @@ class DppHandle:
         self._check(self._lib.dpp_force_kernel_family(self._h, family), "dpp_force_kernel_family")
 
     def set_params(self, k1: float, k2: float, beta: float, mu: float):
-        self._check(self._lib.dpp_set_params(self._h, float(k1), float(k2), float(beta), float(mu)), "dpp_set_params")
+        """dpp_set_params -- skipped when the handle already holds exactly these values (the call invalidates
+        the diagonal, the boundary classification and the captured CUDA graphs of the handle)."""
+        prm = (float(k1), float(k2), float(beta), float(mu))
+        if self._uploaded.get("params") == prm:
+            return
+        self._check(self._lib.dpp_set_params(self._h, *prm), "dpp_set_params")
+        self._uploaded["params"] = prm
 
     def set_dirichlet(self, field: int, nodes: Sequence[int], values: Sequence[float]):
+        """dpp_set_dirichlet -- skipped when nodes and values are unchanged since the last upload."""
         nodes = np.ascontiguousarray(nodes, dtype=np.int32)
         values = np.ascontiguousarray(values, dtype=np.float64)
         if nodes.shape != values.shape:
             raise ValueError("nodes and values must have the same length")
+        old = self._uploaded.get(("bc", int(field)))
+        if old is not None and old[0].shape == nodes.shape and np.array_equal(old[0], nodes) and np.array_equal(old[1], values):
+            return
         self._check(self._lib.dpp_set_dirichlet(self._h, field, nodes.size, _ptr(nodes), _ptr(values)),
                     "dpp_set_dirichlet")
+        self._uploaded[("bc", int(field))] = (nodes.copy(), values.copy())
 
     def comm_init(self, rank: int, world: int, unique_id: Optional[bytes], owned_begin: int, owned_end: int):
         buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
@@ -139,6 +151,12 @@ class DppHandle:
 
     def comm_ipc_disable(self) -> None:
         self._check(self._lib.dpp_comm_ipc_disable(self._h), "dpp_comm_ipc_disable")
+
+    def fused_cg_supported(self) -> bool:
+        return self._lib.dpp_fused_cg_supported(self._h) == 1
+
+    def set_fused_cg(self, enable: bool) -> None:
+        self._check(self._lib.dpp_set_fused_cg(self._h, 1 if enable else 0), "dpp_set_fused_cg")
 
     # -- operator
     def apply(self, x: np.ndarray, assembled: bool = False) -> np.ndarray:
@@ -172,6 +190,32 @@ class DppHandle:
             A.sort_indices()
             return A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data
         return indptr, indices, data
+
+    def assemble_csr_block(self, row_field: int, col_field: int):
+        """Block (row_field, col_field) of the assembled matrix as a scalar-space CSR triplet."""
+        nnz = C.c_int64()
+        self._check(self._lib.dpp_assemble_csr(self._h, C.byref(nnz)), "dpp_assemble_csr")
+        n = self.n_nodes
+        indptr = np.empty(n + 1, dtype=np.int64)
+        indices = np.empty(nnz.value // 4, dtype=np.int32)
+        data = np.empty(nnz.value // 4, dtype=np.float64)
+        self._check(self._lib.dpp_get_csr_block_host(self._h, int(row_field), int(col_field), _ptr(indptr), _ptr(indices),
+                                                     _ptr(data)), "dpp_get_csr_block_host")
+        if self._perm is not None:
+            import scipy.sparse as sp
+
+            pm = self._perm.astype(np.int64)
+            A = sp.csr_matrix((data, indices, indptr), shape=(n, n))[pm][:, pm].tocsr()
+            A.sort_indices()
+            return A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data
+        return indptr, indices, data
+
+    def time_assembly(self, reps: int = 3):
+        """(symbolic_ms, numeric_ms, nnz): device time of the two CSR assembly phases."""
+        a, b, nnz = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self._lib.dpp_time_assembly(self._h, int(reps), C.byref(a), C.byref(b), C.byref(nnz)),
+                    "dpp_time_assembly")
+        return a.value, b.value, nnz.value
 
     # -- solve
     def default_options(self) -> L.DppOptions:

@@ -13,7 +13,7 @@ import numpy as np
 from scipy.sparse import csr_matrix
 
 from .forms import DPPForm
-from .provider import bc_data
+from .provider import bc_data, is_mixed
 from .solver import handle_for
 
 
@@ -36,12 +36,21 @@ def assemble_bilinear_form(form: DPPForm, boundary_conditions: List):
     W = form.space
     if form.rank != 2:
         raise ValueError("assemble_bilinear_form expects a rank-2 form")
-    monolithic = hasattr(W, "num_sub_spaces") and W.num_sub_spaces() == 2
-    if not monolithic:
-        raise NotImplementedError("assemble per-scale blocks by slicing the monolithic CSR (iterative_bench.py:323-324)")
     prm = form.params
     h = handle_for(W)
     h.set_params(float(prm.k1), float(prm.k2), float(prm.beta), float(prm.mu))
+    if not is_mixed(W):
+        # per-scale form of dpp_delayed_form on a scalar space V (forms/dpp.py:135-205; assembled with its own
+        # scalar BC at notebooks/conforming-galerkin-fem-operator-splitting-2D-perphil.py:463-480): the diagonal
+        # block (f, f) of the V x V matrix, assembled and extracted on the GPU
+        if len(form.blocks) != 1 or form.blocks[0][0] != form.blocks[0][1]:
+            raise ValueError("a form on a scalar space must denote one diagonal block (dpp_delayed_form)")
+        f = form.blocks[0][0]
+        got = {fl: (n, v) for fl, n, v in bc_data(W, boundary_conditions, scalar_field=f)}
+        n, v = got.get(f, (np.zeros(0, np.int32), np.zeros(0)))
+        h.set_dirichlet(f, n, v)
+        h.set_dirichlet(1 - f, np.zeros(0, np.int32), np.zeros(0))
+        return h.assemble_csr_block(f, f)
     got = {f: (n, v) for f, n, v in bc_data(W, boundary_conditions)}
     for f in (0, 1):
         n, v = got.get(f, (np.zeros(0, np.int32), np.zeros(0)))

@@ -10,10 +10,15 @@
 //   The monolithic pattern is the node graph replicated in 2x2 blocks: row r of field f holds
 //   [cols(r), n + cols(r)], columns sorted -- the full element pattern PETSc preallocates.
 // Numeric phase (per parameter / Dirichlet change, fp64, no atomics, bitwise reproducible):
-//   one thread owns one node-graph row for both fields, accumulates K_e[a][b], M_e[a][b] of its
-//   incident cells through pos[], then writes the four block segments with Firedrake's Dirichlet
-//   semantics (constrained rows/columns zeroed, unit diagonal; explicit zeros stay in the pattern,
-//   conditioning.py:86 removes them on the host).
+//   a group of LANES >= nodes_per_cell lanes owns one node-graph row for both fields.  The incident
+//   cells are visited in ascending order; lane b adds K_e[a][b], M_e[a][b] into slot pos[cell][a][b]
+//   of a shared-memory row buffer (the slots of one cell are distinct: no conflicts, fixed order);
+//   non-affine cells first tabulate the metric at the (P+1)^dim Gauss points, one point per lane.
+//   The group then writes the four block segments of the row with consecutive lanes on consecutive
+//   entries (coalesced), with Firedrake's Dirichlet semantics (constrained rows/columns zeroed, unit
+//   diagonal; explicit zeros stay in the pattern, conditioning.py:86 removes them on the host).
+//   Bytes: writes 8 B per entry; reads the permutation (1 B per (cell, a, b)), the node graph and
+//   the column masks.
 #include <algorithm>
 #include <vector>
 
@@ -74,24 +79,78 @@ __global__ void k_graph_rows(long long n, const int64_t* __restrict__ adj_ptr, c
   }
 }
 
-__global__ void k_exclusive_scan_serial(long long n, const int64_t* __restrict__ counts, int64_t* __restrict__ ptr) {
-  // single block, chunked: each thread scans a contiguous chunk, then offsets are combined
-  __shared__ long long sums[1024];
-  const int t = threadIdx.x, nt = blockDim.x;
-  const long long per = (n + nt - 1) / nt;
-  const long long b = (long long)t * per, e = b + per < n ? b + per : n;
-  long long s = 0;
-  for (long long i = b; i < e; ++i) s += counts[i];
-  sums[t] = s;
-  __syncthreads();
-  if (t == 0) {
-    long long acc = 0;
-    for (int i = 0; i < nt; ++i) { const long long v = sums[i]; sums[i] = acc; acc += v; }
-    ptr[n] = acc;
+// exclusive scan in three phases (deterministic integer work): per-block sums, scan of the block sums by one
+// block, per-block scan with the block offset added
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;                      // items per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ long long block_exclusive_scan(long long v, long long* total, long long* sm /*[SCAN_THREADS/32 + 1]*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
   __syncthreads();
-  long long acc = sums[t];
-  for (long long i = b; i < e; ++i) { ptr[i] = acc; acc += counts[i]; }
+  if (lane == 31) sm[wid] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long acc = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) { const long long t = sm[w]; sm[w] = acc; acc += t; }
+    sm[SCAN_THREADS / 32] = acc;
+  }
+  __syncthreads();
+  *total = sm[SCAN_THREADS / 32];
+  return sm[wid] + incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_block_sums(long long n, const int64_t* __restrict__ counts,
+                                                                  int64_t* __restrict__ block_sums) {
+  __shared__ long long sm[SCAN_THREADS / 32 + 1];
+  const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  long long s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < n) s += counts[base + i];
+  long long total;
+  block_exclusive_scan(s, &total, sm);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// in-place exclusive scan of the block sums by one block (chunked over its threads); sums[nb] = grand total
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(long long nb, int64_t* __restrict__ sums) {
+  __shared__ long long sm[SCAN_THREADS / 32 + 1];
+  const long long per = (nb + SCAN_THREADS - 1) / SCAN_THREADS;
+  const long long b = (long long)threadIdx.x * per, e = b + per < nb ? b + per : nb;
+  long long s = 0;
+  for (long long i = b; i < e; ++i) s += sums[i];
+  long long total;
+  long long acc = block_exclusive_scan(s, &total, sm);
+  for (long long i = b; i < e; ++i) { const long long v = sums[i]; sums[i] = acc; acc += v; }
+  if (threadIdx.x == 0) sums[nb] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_finish(long long n, const int64_t* __restrict__ counts,
+                                                              const int64_t* __restrict__ block_offs,
+                                                              int64_t* __restrict__ ptr) {
+  __shared__ long long sm[SCAN_THREADS / 32 + 1];
+  const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  long long v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = base + i < n ? counts[base + i] : 0;
+    s += v[i];
+  }
+  long long total;
+  long long acc = block_exclusive_scan(s, &total, sm) + block_offs[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < n) ptr[base + i] = acc;
+    acc += v[i];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) ptr[n] = block_offs[gridDim.x];
 }
 
 template <int NPC>
@@ -153,78 +212,100 @@ struct NumArgs {
   double* data;
 };
 
+constexpr int NUM_THREADS = 128;
+
+// LANES lanes per node-graph row (LANES = nodes per cell rounded up to a power of two, <= 32)
 template <int DIM, int P>
-__global__ void __launch_bounds__(128) k_numeric(const NumArgs g) {
+__global__ void __launch_bounds__(NUM_THREADS) k_numeric(const NumArgs g) {
   constexpr int P1 = P + 1;
   constexpr int NPC = DIM == 2 ? P1 * P1 : P1 * P1 * P1;
+  constexpr int LANES = NPC <= 4 ? 4 : NPC <= 8 ? 8 : NPC <= 16 ? 16 : 32;
   constexpr int MAXROW = DIM == 2 ? (2 * P + 1) * (2 * P + 1) : (2 * P + 1) * (2 * P + 1) * (2 * P + 1);
-  constexpr int NQ = P1, NV = 1 << DIM, Q0N = DIM == 2 ? 1 : NQ;
-  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (r >= g.n) return;
-  double accK[MAXROW], accM[MAXROW];
-  const long long gb = g.g_ptr[r];
-  const int len = (int)(g.g_ptr[r + 1] - gb);
-  for (int t = 0; t < MAXROW; ++t) accK[t] = accM[t] = 0.0;
-  for (long long e = g.adj_ptr[r]; e < g.adj_ptr[r + 1]; ++e) {
+  constexpr int ROWS = NUM_THREADS / LANES;   // rows per block
+  constexpr int NQ = P1, NV = 1 << DIM, NQP = NPC;   // (P+1)^dim Gauss points = one per lane b < NPC
+  __shared__ double sK[ROWS][MAXROW], sM[ROWS][MAXROW];
+  __shared__ double sG[ROWS][NQP][7];        // metric at the Gauss points of the current (non-affine) cell
+  const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+  const long long r = (long long)blockIdx.x * ROWS + grp;
+  // the lanes of one group live in one warp: group-wide synchronisation = __syncwarp on the group's mask
+  const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
+  const bool live = r < g.n;
+  for (int t = lane; t < MAXROW; t += LANES) sK[grp][t] = sM[grp][t] = 0.0;
+  __syncwarp(gmask);
+  const long long e0 = live ? g.adj_ptr[r] : 0, e1 = live ? g.adj_ptr[r + 1] : 0;
+  int b0 = 0, b1 = 0, b2 = 0;   // lane as trial node b / as Gauss point q
+  if (DIM == 2) { b1 = lane / P1; b2 = lane % P1; }
+  else { b0 = lane / (P1 * P1); b1 = (lane / P1) % P1; b2 = lane % P1; }
+  for (long long e = e0; e < e1; ++e) {
     const long long cell = g.adj_cell[e];
     const int a = g.adj_loc[e];
     const double* gm = g.geom + cell * 8;
-    const uint8_t* pp = g.pos + (cell * NPC + a) * NPC;
+    double kab = 0.0, mab = 0.0;
     if (gm[7] != 0.0) {  // affine cell: constant metric x reference integrals
-      for (int b = 0; b < NPC; ++b) {
-        const int ab = a * NPC + b;
-        double kab = 0.0;
+      if (lane < NPC) {
+        const int ab = a * NPC + lane;
 #pragma unroll
         for (int s = 0; s < 6; ++s) kab = fma(gm[s], cTK[s * 729 + ab], kab);
-        const int p = pp[b];
-        accK[p] += kab;
-        accM[p] += gm[6] * cTM[ab];
+        mab = gm[6] * cTM[ab];
       }
-    } else {  // general cell: Gauss quadrature of the multilinear map
-      int a0, a1, a2;
-      if (DIM == 2) { a0 = 0; a1 = a / P1; a2 = a % P1; }
-      else { a0 = a / (P1 * P1); a1 = (a / P1) % P1; a2 = a % P1; }
-      for (int q0 = 0; q0 < Q0N; ++q0)
-        for (int q1 = 0; q1 < NQ; ++q1)
-          for (int q2 = 0; q2 < NQ; ++q2) {
-            const double wq = (DIM == 2 ? 1.0 : cW[P - 1][q0]) * cW[P - 1][q1] * cW[P - 1][q2];
-            double J[3][3], Gq[3][3], dm;
-            jacobian_at<DIM, P>(g.coords, g.ccnm + cell * NV, DIM == 2 ? q1 : q0, DIM == 2 ? q2 : q1, q2, J);
-            metric_from_J<DIM>(J, wq, Gq, dm);
-            const double Ba0 = DIM == 2 ? 1.0 : cB[P - 1][a0][q0], Da0 = DIM == 2 ? 0.0 : cD[P - 1][a0][q0];
-            const double Ba1 = cB[P - 1][a1][q1], Da1 = cD[P - 1][a1][q1];
-            const double Ba2 = cB[P - 1][a2][q2], Da2 = cD[P - 1][a2][q2];
-            const double ta = Ba0 * Ba1 * Ba2;
-            double gta[3];
-            if (DIM == 2) { gta[0] = Da1 * Ba2; gta[1] = Ba1 * Da2; gta[2] = 0.0; }
-            else { gta[0] = Da0 * Ba1 * Ba2; gta[1] = Ba0 * Da1 * Ba2; gta[2] = Ba0 * Ba1 * Da2; }
-            double Gt[3];
-            for (int rr = 0; rr < 3; ++rr) Gt[rr] = Gq[rr][0] * gta[0] + Gq[rr][1] * gta[1] + Gq[rr][2] * gta[2];
-            for (int b = 0; b < NPC; ++b) {
-              int b0, b1, b2;
-              if (DIM == 2) { b0 = 0; b1 = b / P1; b2 = b % P1; }
-              else { b0 = b / (P1 * P1); b1 = (b / P1) % P1; b2 = b % P1; }
+    } else {             // general cell: Gauss quadrature of the multilinear map
+      if (lane < NQP) {  // lane = Gauss point (q0, q1, q2) = (b0, b1, b2)
+        const double wq = (DIM == 2 ? 1.0 : cW[P - 1][b0]) * cW[P - 1][b1] * cW[P - 1][b2];
+        double J[3][3], Gq[3][3], dm;
+        jacobian_at<DIM, P>(g.coords, g.ccnm + cell * NV, DIM == 2 ? b1 : b0, DIM == 2 ? b2 : b1, b2, J);
+        metric_from_J<DIM>(J, wq, Gq, dm);
+        double* o = sG[grp][lane];
+        o[0] = Gq[0][0]; o[1] = Gq[0][1]; o[2] = Gq[0][2]; o[3] = Gq[1][1]; o[4] = Gq[1][2]; o[5] = Gq[2][2]; o[6] = dm;
+      }
+      __syncwarp(gmask);
+      if (lane < NPC) {
+        int a0, a1, a2;
+        if (DIM == 2) { a0 = 0; a1 = a / P1; a2 = a % P1; }
+        else { a0 = a / (P1 * P1); a1 = (a / P1) % P1; a2 = a % P1; }
+        for (int q0 = 0; q0 < (DIM == 2 ? 1 : NQ); ++q0)
+          for (int q1 = 0; q1 < NQ; ++q1)
+            for (int q2 = 0; q2 < NQ; ++q2) {
+              const double* o = sG[grp][DIM == 2 ? q1 * NQ + q2 : (q0 * NQ + q1) * NQ + q2];
+              const double Ba0 = DIM == 2 ? 1.0 : cB[P - 1][a0][q0], Da0 = DIM == 2 ? 0.0 : cD[P - 1][a0][q0];
+              const double Ba1 = cB[P - 1][a1][q1], Da1 = cD[P - 1][a1][q1];
+              const double Ba2 = cB[P - 1][a2][q2], Da2 = cD[P - 1][a2][q2];
               const double Bb0 = DIM == 2 ? 1.0 : cB[P - 1][b0][q0], Db0 = DIM == 2 ? 0.0 : cD[P - 1][b0][q0];
               const double Bb1 = cB[P - 1][b1][q1], Db1 = cD[P - 1][b1][q1];
               const double Bb2 = cB[P - 1][b2][q2], Db2 = cD[P - 1][b2][q2];
-              double gtb[3];
-              if (DIM == 2) { gtb[0] = Db1 * Bb2; gtb[1] = Bb1 * Db2; gtb[2] = 0.0; }
-              else { gtb[0] = Db0 * Bb1 * Bb2; gtb[1] = Bb0 * Db1 * Bb2; gtb[2] = Bb0 * Bb1 * Db2; }
-              const int p = pp[b];
-              accK[p] += Gt[0] * gtb[0] + Gt[1] * gtb[1] + Gt[2] * gtb[2];
-              accM[p] += ta * (Bb0 * Bb1 * Bb2) * dm;
+              double gta[3], gtb[3];
+              if (DIM == 2) {
+                gta[0] = Da1 * Ba2; gta[1] = Ba1 * Da2; gta[2] = 0.0;
+                gtb[0] = Db1 * Bb2; gtb[1] = Bb1 * Db2; gtb[2] = 0.0;
+              } else {
+                gta[0] = Da0 * Ba1 * Ba2; gta[1] = Ba0 * Da1 * Ba2; gta[2] = Ba0 * Ba1 * Da2;
+                gtb[0] = Db0 * Bb1 * Bb2; gtb[1] = Bb0 * Db1 * Bb2; gtb[2] = Bb0 * Bb1 * Db2;
+              }
+              const double Gt0 = o[0] * gta[0] + o[1] * gta[1] + o[2] * gta[2];
+              const double Gt1 = o[1] * gta[0] + o[3] * gta[1] + o[4] * gta[2];
+              const double Gt2 = o[2] * gta[0] + o[4] * gta[1] + o[5] * gta[2];
+              kab += Gt0 * gtb[0] + Gt1 * gtb[1] + Gt2 * gtb[2];
+              mab += (Ba0 * Ba1 * Ba2) * (Bb0 * Bb1 * Bb2) * o[6];
             }
-          }
+      }
     }
+    if (lane < NPC) {   // the NPC slots of one (cell, a) are distinct: conflict-free, cells in ascending order
+      const int p = g.pos[(cell * NPC + a) * NPC + lane];
+      sK[grp][p] += kab;
+      sM[grp][p] += mab;
+    }
+    __syncwarp(gmask);
   }
-  // write the four block segments of rows r (field 0) and n + r (field 1)
+  if (!live) return;
+  // write the four block segments of rows r (field 0) and n + r (field 1): consecutive lanes, consecutive entries
+  const long long gb = g.g_ptr[r];
+  const int len = (int)(g.g_ptr[r + 1] - gb);
   const long long n = g.n;
   const bool m0 = g.mask[r] != 0, m1 = g.mask[n + r] != 0;
   const long long p0 = 2 * gb, p1 = 2 * g.nnz_g + 2 * gb;
-  for (int t = 0; t < len; ++t) {
+  for (int t = lane; t < len; t += LANES) {
     const long long c = g.g_cols[gb + t];
     const bool c0 = g.mask[c] != 0, c1 = g.mask[n + c] != 0;
-    const double K = accK[t], M = accM[t];
+    const double K = sK[grp][t], M = sM[grp][t];
     const bool diag = (c == r);
     double v00 = g.c.cK[0][0] * K + g.c.cM[0][0] * M, v01 = g.c.cK[0][1] * K + g.c.cM[0][1] * M;
     double v10 = g.c.cK[1][0] * K + g.c.cM[1][0] * M, v11 = g.c.cK[1][1] * K + g.c.cM[1][1] * M;
@@ -236,6 +317,18 @@ __global__ void __launch_bounds__(128) k_numeric(const NumArgs g) {
     g.data[p0 + len + t] = v01;
     g.data[p1 + t] = v10;
     g.data[p1 + len + t] = v11;
+  }
+}
+
+// one diagonal-or-coupling block (row field fr, column field fc) of the assembled matrix as a scalar-space CSR
+// matrix: pattern = the node graph, values gathered from the monolithic storage
+__global__ void k_extract_block(long long n, long long nnz_g, const int64_t* __restrict__ g_ptr,
+                                const double* __restrict__ data, int fr, int fc, double* __restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const long long gb = g_ptr[r];
+    const int len = (int)(g_ptr[r + 1] - gb);
+    const double* src = data + (fr ? 2 * nnz_g : 0) + 2 * gb + (fc ? len : 0);
+    for (int t = 0; t < len; ++t) out[gb + t] = src[t];
   }
 }
 
@@ -354,9 +447,19 @@ int symbolic(dpp_context* ctx, CsrMatrix* A) {
 #undef GRAPH_CASE
   graph(counts, nullptr, nullptr);
   DPP_CUDA(cudaGetLastError());
-  k_exclusive_scan_serial<<<1, 1024, 0, ctx->stream>>>(n, counts, A->g_ptr);
-  ctx->launches++;
-  DPP_CUDA(cudaGetLastError());
+  {
+    const long long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    int64_t* sums = nullptr;
+    DPP_CHECK(dev_alloc(ctx, &sums, nb + 1));
+    k_scan_block_sums<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(n, counts, sums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, ctx->stream>>>(nb, sums);
+    k_scan_finish<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(n, counts, sums, A->g_ptr);
+    ctx->launches += 3;
+    DPP_CUDA(cudaGetLastError());
+    DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(sums);
+    ctx->device_bytes -= (int64_t)sizeof(int64_t) * (nb + 1);
+  }
   int64_t nnz_g = 0;
   DPP_CUDA(cudaMemcpyAsync(&nnz_g, A->g_ptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   DPP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -396,12 +499,15 @@ int numeric(dpp_context* ctx, CsrMatrix* A) {
   g.cnm = ctx->d_cnm; g.ccnm = ctx->d_ccnm; g.coords = ctx->d_coords; g.geom = ctx->d_cell_geom;
   g.pos = A->pos; g.g_ptr = A->g_ptr; g.g_cols = A->g_cols; g.mask = ctx->d_mask;
   g.n = ctx->n_nodes; g.nnz_g = A->nnz_g; g.c = dpp_coef(ctx); g.data = A->data;
-  const int blocks = (int)((ctx->n_nodes + 127) / 128);
   const int dim = ctx->dim, p = ctx->degree;
-  if (dim == 2 && p == 1) k_numeric<2, 1><<<blocks, 128, 0, ctx->stream>>>(g);
-  else if (dim == 2 && p == 2) k_numeric<2, 2><<<blocks, 128, 0, ctx->stream>>>(g);
-  else if (dim == 3 && p == 1) k_numeric<3, 1><<<blocks, 128, 0, ctx->stream>>>(g);
-  else k_numeric<3, 2><<<blocks, 128, 0, ctx->stream>>>(g);
+  const int npc = ctx->npc;
+  const int lanes = npc <= 4 ? 4 : npc <= 8 ? 8 : npc <= 16 ? 16 : 32;
+  const int rows = NUM_THREADS / lanes;
+  const unsigned blocks = (unsigned)((ctx->n_nodes + rows - 1) / rows);
+  if (dim == 2 && p == 1) k_numeric<2, 1><<<blocks, NUM_THREADS, 0, ctx->stream>>>(g);
+  else if (dim == 2 && p == 2) k_numeric<2, 2><<<blocks, NUM_THREADS, 0, ctx->stream>>>(g);
+  else if (dim == 3 && p == 1) k_numeric<3, 1><<<blocks, NUM_THREADS, 0, ctx->stream>>>(g);
+  else k_numeric<3, 2><<<blocks, NUM_THREADS, 0, ctx->stream>>>(g);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   A->numeric_valid = true;
@@ -462,6 +568,62 @@ int csr_spmv(dpp_context* ctx, const double* x, double* y, double* dot_partials,
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   if (n_partial_blocks) *n_partial_blocks = blocks;
+  return DPP_OK;
+}
+
+// block (fr, fc) as a scalar-space CSR triplet: indptr [n+1], indices / data [nnz / 4]
+int csr_export_block(dpp_context* ctx, int fr, int fc, int64_t* indptr, int32_t* indices, double* data) {
+  CsrMatrix* A = ctx->csr;
+  if (!A || !A->numeric_valid) {
+    ctx->set_error("dpp_get_csr_block_host: call dpp_assemble_csr first");
+    return DPP_ERR_STATE;
+  }
+  const long long n = A->n_nodes;
+  if (indptr) DPP_CUDA(cudaMemcpyAsync(indptr, A->g_ptr, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  if (indices) DPP_CUDA(cudaMemcpyAsync(indices, A->g_cols, sizeof(int32_t) * A->nnz_g, cudaMemcpyDeviceToHost, ctx->stream));
+  if (data) {
+    double* tmp = nullptr;
+    DPP_CHECK(dev_alloc(ctx, &tmp, A->nnz_g));
+    k_extract_block<<<blocks_for(ctx, n, 128), 128, 0, ctx->stream>>>(n, A->nnz_g, A->g_ptr, A->data, fr, fc, tmp);
+    ctx->launches++;
+    DPP_CUDA(cudaGetLastError());
+    DPP_CUDA(cudaMemcpyAsync(data, tmp, sizeof(double) * A->nnz_g, cudaMemcpyDeviceToHost, ctx->stream));
+    DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+    ctx->device_bytes -= (int64_t)sizeof(double) * A->nnz_g;
+  }
+  DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DPP_OK;
+}
+
+// measurement: device milliseconds of the symbolic phase (pattern + scatter permutation, rebuilt from scratch)
+// and of the numeric phase (mean of `reps` fills)
+int csr_time_phases(dpp_context* ctx, int reps, double* symbolic_ms, double* numeric_ms, int64_t* nnz) {
+  if (!ctx->general_ready) {
+    std::vector<int32_t> cnm((size_t)ctx->n_cells * ctx->npc);
+    DPP_CUDA(cudaMemcpy(cnm.data(), ctx->d_cnm, sizeof(int32_t) * cnm.size(), cudaMemcpyDeviceToHost));
+    DPP_CHECK(general_setup(ctx, cnm.data()));
+  }
+  csr_destroy(ctx);
+  ctx->csr = new CsrMatrix();
+  DPP_CHECK(upload_reference_tables(ctx));
+  cudaEvent_t ev[4];
+  for (auto& e : ev) DPP_CUDA(cudaEventCreate(&e));
+  DPP_CUDA(cudaEventRecord(ev[0], ctx->stream));
+  DPP_CHECK(symbolic(ctx, ctx->csr));
+  DPP_CUDA(cudaEventRecord(ev[1], ctx->stream));
+  DPP_CHECK(numeric(ctx, ctx->csr));   // warm-up
+  DPP_CUDA(cudaEventRecord(ev[2], ctx->stream));
+  for (int i = 0; i < std::max(reps, 1); ++i) DPP_CHECK(numeric(ctx, ctx->csr));
+  DPP_CUDA(cudaEventRecord(ev[3], ctx->stream));
+  DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  float a = 0, b = 0;
+  cudaEventElapsedTime(&a, ev[0], ev[1]);
+  cudaEventElapsedTime(&b, ev[2], ev[3]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (symbolic_ms) *symbolic_ms = a;
+  if (numeric_ms) *numeric_ms = b / std::max(reps, 1);
+  if (nnz) *nnz = ctx->csr->nnz;
   return DPP_OK;
 }
 

@@ -729,6 +729,7 @@ void cg_fused_destroy(dpp_context* ctx) {
 
 bool cg_fused_available(const dpp_context* ctx, int nf, int operator_mode, int pc_type) {
   return ctx->family == DPP_KERNEL_STRUCTURED && ctx->grid.band == 1 && ctx->grid_uniform && !ctx->force_table_kernel &&
+         !ctx->fused_cg_disabled &&
          operator_mode == DPP_OP_MATRIX_FREE && (pc_type == DPP_PC_NONE || pc_type == DPP_PC_JACOBI) &&
          (nf == 1 || nf == 2) && getenv("DPP_NO_FUSED_CG") == nullptr && encode_fn() != nullptr;
 }

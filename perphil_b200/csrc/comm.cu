@@ -195,16 +195,24 @@ int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n) {
 bool comm_ipc_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc; }
 bool comm_ipc_halo_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc && ctx->comm->ipc_halo; }
 
-// Measurement switches that deliberately break the protocol (profiles/r01_exchange_cost.md): never silent.
+// Measurement switches that deliberately break the protocol (profiles/r01_exchange_cost.md) exist only in
+// builds made with -DDPP_MEASUREMENT (make MEASUREMENT=1); the release library ignores the variables, so
+// no benchmark number can be taken with wrong numerics by accident.
+#ifdef DPP_MEASUREMENT
 static void warn_measurement_switches() {
   static bool done = false;
   if (done) return;
   done = true;
   const char* ll = getenv("DPP_MBOX_LL");
   if (getenv("DPP_DEBUG_NO_MBOX") || getenv("DPP_DEBUG_NO_PUSH") || (ll != nullptr && atoi(ll) == 2))
-    fprintf(stderr, "libdppb200: DPP_DEBUG_NO_MBOX / DPP_DEBUG_NO_PUSH / DPP_MBOX_LL=2 are timing experiments: "
-                    "the multi-GPU RESULTS OF THIS RUN ARE INVALID\n");
+    fprintf(stderr, "libdppb200 (DPP_MEASUREMENT build): DPP_DEBUG_NO_MBOX / DPP_DEBUG_NO_PUSH / DPP_MBOX_LL=2 are "
+                    "timing experiments: the multi-GPU RESULTS OF THIS RUN ARE INVALID\n");
 }
+static bool meas_env(const char* name) { return getenv(name) != nullptr; }
+#else
+static void warn_measurement_switches() {}
+static bool meas_env(const char*) { return false; }
+#endif
 
 IpcReduce comm_ipc_reduce_args(dpp_context* ctx) {
   warn_measurement_switches();
@@ -215,25 +223,32 @@ IpcReduce comm_ipc_reduce_args(dpp_context* ctx) {
   a.local = C->mbox;
   for (int r = 0; r < ctx->world; ++r) a.peer[r] = (r == ctx->rank) ? C->mbox : C->mbox_peer[r];
   a.rank = ctx->rank;
-  a.world = getenv("DPP_DEBUG_NO_MBOX") ? 1 : ctx->world;   // timing experiments only: local sums
+  a.world = meas_env("DPP_DEBUG_NO_MBOX") ? 1 : ctx->world;   // timing experiments only: local sums
   // the sequence counter lives behind the mailbox entries; it advances only when an exchange really runs
   a.seq_dev = reinterpret_cast<unsigned long long*>(C->mbox + 2 * kMaxIpcRanks * kMboxWords);
-  const char* ll = getenv("DPP_MBOX_LL");
-  a.ll = (ll != nullptr) ? atoi(ll) : 1;
+  a.ll = 1;   // tagged words (cg_device.cuh); 0 = values + fence + flag word (valid, slower), 3 = fence for <p,Ap> too
+#ifdef DPP_MEASUREMENT
+  if (const char* ll = getenv("DPP_MBOX_LL")) a.ll = atoi(ll);
+#else
+  if (const char* ll = getenv("DPP_MBOX_LL")) {   // only the protocol-correct variants are selectable
+    const int v = atoi(ll);
+    if (v == 0 || v == 1 || v == 3) a.ll = v;
+  }
+#endif
   return a;
 }
 
 IpcHalo comm_ipc_halo(const dpp_context* ctx) {
   IpcHalo h{};
   const Comm* C = ctx->comm;
-  // DPP_DEBUG_NO_PUSH: timing experiments only (the solve is wrong without the ghost planes)
-  if (C && C->ipc && C->ipc_halo && getenv("DPP_DEBUG_NO_PUSH") == nullptr)
+  // DPP_DEBUG_NO_PUSH (measurement builds only): the solve is wrong without the ghost planes
+  if (C && C->ipc && C->ipc_halo && !meas_env("DPP_DEBUG_NO_PUSH"))
     for (int s = 0; s < 2; ++s) {
       h.peer_r[s] = C->r_peer[s];
       h.peer_field[s] = C->r_peer_field[s];
       h.peer_ghost_off[s] = C->r_peer_ghost_off[s];
     }
-  h.debug_fence_all = getenv("DPP_DEBUG_FENCE_ALL") != nullptr;
+  h.debug_fence_all = meas_env("DPP_DEBUG_FENCE_ALL");
   return h;
 }
 

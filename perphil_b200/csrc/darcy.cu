@@ -7,12 +7,18 @@
 // multilinear cell geometry (any numbering, any cell shape; exact on parallelepiped cells), and (2) dim
 // Jacobi-CG solves with the nodal mass matrix (krylov_mass_solve: the handle's matrix-free operator with
 // coefficient block cK = 0, cM = 1 and no Dirichlet rows).
-// The cell loop scatters with fp64 atomicAdd (at most 2^dim addends per vertex node): values are
-// reproducible to rounding, not bitwise -- this is post-processing, not the assembly path.
+// No atomics: the cell kernel stores its NPC x dim element load vector into a per-cell scratch array and a
+// row-owner gather (one thread per node, incident cells in ascending order through the node -> (cell, local)
+// adjacency the CSR assembly and the general apply use) adds them in a fixed order: bitwise reproducible
+// like every other kernel of the library.
+#include <algorithm>
+#include <vector>
+
 #include "fe_common.cuh"
 
 namespace dpp {
 
+int general_setup(dpp_context* ctx, const int32_t* cnm);
 int krylov_mass_solve(dpp_context* ctx, const double* d_rhs, double* d_out, double rtol, int max_it, int* its,
                       double* rnorm, int* reason);
 
@@ -25,7 +31,7 @@ struct GradArgs {
   const double* coords;
   const double* p;     // [n_nodes] nodal pressure
   double scale;        // -k
-  double* out;         // [dim][n_nodes], zeroed
+  double* cell_out;    // [n_cells][NPC][dim] element load vectors
 };
 
 template <int DIM, int P>
@@ -95,9 +101,29 @@ __global__ void __launch_bounds__(128) k_grad_load(const GradArgs a) {
           for (int d = 0; d < DIM; ++d) be[b][d] = fma(N, gd[d], be[b][d]);
         }
       }
-  for (int b = 0; b < NPC; ++b) {
-    const long long nb = a.cnm[cell * NPC + b];
-    for (int d = 0; d < DIM; ++d) atomicAdd(a.out + d * a.n_nodes + nb, be[b][d]);
+  double* o = a.cell_out + cell * (NPC * DIM);
+  for (int b = 0; b < NPC; ++b)
+    for (int d = 0; d < DIM; ++d) o[b * DIM + d] = be[b][d];
+}
+
+// b_c[node] = sum over the incident cells (ascending cell order) of their element load vector entry
+template <int DIM>
+__global__ void __launch_bounds__(256) k_grad_gather(long long n_nodes, int npc, const int64_t* __restrict__ adj_ptr,
+                                                     const int32_t* __restrict__ adj_cell,
+                                                     const uint8_t* __restrict__ adj_loc,
+                                                     const double* __restrict__ cell_out, double* __restrict__ out) {
+  for (long long node = blockIdx.x * (long long)blockDim.x + threadIdx.x; node < n_nodes;
+       node += (long long)gridDim.x * blockDim.x) {
+    double acc[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) acc[d] = 0.0;
+    for (long long e = adj_ptr[node]; e < adj_ptr[node + 1]; ++e) {
+      const double* o = cell_out + ((long long)adj_cell[e] * npc + adj_loc[e]) * DIM;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) acc[d] += o[d];
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) out[d * n_nodes + node] = acc[d];
   }
 }
 
@@ -109,8 +135,14 @@ int darcy_velocity(dpp_context* ctx, const double* d_p, double conductivity, dou
                    double* d_vel, int32_t* iterations, double* residuals) {
   DPP_CHECK(fe_upload_tables(ctx));   // this translation unit's copy of the constant tabulations
   const long long n = ctx->n_nodes;
-  DPP_CUDA(cudaMemsetAsync(d_rhs, 0, sizeof(double) * ctx->dim * n, ctx->stream));
-  GradArgs a{ctx->n_cells, n, ctx->d_cnm, ctx->d_ccnm, ctx->d_coords, d_p, -conductivity, d_rhs};
+  if (!ctx->general_ready) {  // node -> (cell, local) adjacency lives with the general family
+    std::vector<int32_t> cnm((size_t)ctx->n_cells * ctx->npc);
+    DPP_CUDA(cudaMemcpy(cnm.data(), ctx->d_cnm, sizeof(int32_t) * cnm.size(), cudaMemcpyDeviceToHost));
+    DPP_CHECK(general_setup(ctx, cnm.data()));
+  }
+  double* cell_out = nullptr;
+  DPP_CHECK(dev_alloc(ctx, &cell_out, (int64_t)ctx->n_cells * ctx->npc * ctx->dim));
+  GradArgs a{ctx->n_cells, n, ctx->d_cnm, ctx->d_ccnm, ctx->d_coords, d_p, -conductivity, cell_out};
   const int threads = 128;
   const unsigned blocks = (unsigned)((ctx->n_cells + threads - 1) / threads);
   if (ctx->dim == 2 && ctx->degree == 1) k_grad_load<2, 1><<<blocks, threads, 0, ctx->stream>>>(a);
@@ -118,7 +150,16 @@ int darcy_velocity(dpp_context* ctx, const double* d_p, double conductivity, dou
   else if (ctx->degree == 1) k_grad_load<3, 1><<<blocks, threads, 0, ctx->stream>>>(a);
   else k_grad_load<3, 2><<<blocks, threads, 0, ctx->stream>>>(a);
   ctx->launches++;
+  const unsigned gblocks = (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16));
+  if (ctx->dim == 2)
+    k_grad_gather<2><<<gblocks, 256, 0, ctx->stream>>>(n, ctx->npc, ctx->d_adj_ptr, ctx->d_adj_cell, ctx->d_adj_loc, cell_out, d_rhs);
+  else
+    k_grad_gather<3><<<gblocks, 256, 0, ctx->stream>>>(n, ctx->npc, ctx->d_adj_ptr, ctx->d_adj_cell, ctx->d_adj_loc, cell_out, d_rhs);
+  ctx->launches++;
   DPP_CUDA(cudaGetLastError());
+  DPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(cell_out);
+  ctx->device_bytes -= (int64_t)sizeof(double) * ctx->n_cells * ctx->npc * ctx->dim;
   for (int c = 0; c < ctx->dim; ++c) {
     int its = 0, reason = 0;
     double rn = 0.0;

@@ -221,6 +221,18 @@ int dpp_get_info(dpp_handle ctx, dpp_info* info) {
   return DPP_OK;
 }
 
+int dpp_fused_cg_supported(dpp_handle ctx) {
+  if (!ctx) return DPP_ERR_INVALID;
+  return dpp::cg_fused_available(ctx, 2, DPP_OP_MATRIX_FREE, DPP_PC_JACOBI) ? 1 : 0;
+}
+
+int dpp_set_fused_cg(dpp_handle ctx, int enable) {
+  if (!ctx) return DPP_ERR_INVALID;
+  ctx->fused_cg_disabled = enable == 0;
+  ctx->invalidate();
+  return DPP_OK;
+}
+
 int dpp_force_kernel_family(dpp_handle ctx, int family) {
   if (!ctx) return DPP_ERR_INVALID;
   cudaSetDevice(ctx->device);
@@ -406,6 +418,22 @@ int dpp_get_csr_host(dpp_handle ctx, int64_t* indptr, int32_t* indices, double* 
   if (!ctx) return DPP_ERR_INVALID;
   cudaSetDevice(ctx->device);
   return dpp::csr_export(ctx, indptr, indices, data);
+}
+
+int dpp_get_csr_block_host(dpp_handle ctx, int row_field, int col_field, int64_t* indptr, int32_t* indices, double* data) {
+  if (!ctx || row_field < 0 || row_field > 1 || col_field < 0 || col_field > 1) return DPP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  return dpp::csr_export_block(ctx, row_field, col_field, indptr, indices, data);
+}
+
+int dpp_time_assembly(dpp_handle ctx, int reps, double* symbolic_ms, double* numeric_ms, int64_t* nnz) {
+  if (!ctx) return DPP_ERR_INVALID;
+  if (!ctx->have_params) {
+    ctx->set_error("dpp_time_assembly: call dpp_set_params first");
+    return DPP_ERR_STATE;
+  }
+  cudaSetDevice(ctx->device);
+  return dpp::csr_time_phases(ctx, reps, symbolic_ms, numeric_ms, nnz);
 }
 
 void dpp_default_options(dpp_options* o) {

@@ -94,6 +94,7 @@ struct dpp_context {
   std::vector<double> h_axis[3];  // 1-D vertex coordinates per axis (structured)
   bool grid_uniform = false;      // equal spacing on every axis -> apply_structured_uniform.cu
   bool force_table_kernel = false;
+  bool fused_cg_disabled = false;   // dpp_set_fused_cg(h, 0): ranks of a slab run agree on ONE protocol
   double uni_m_off[3] = {0, 0, 0}, uni_k_off[3] = {0, 0, 0};
   double uni_mxc[2] = {0, 0}, uni_kxc[2] = {0, 0};  // axis-0 centre entries [interior, boundary]
 
@@ -153,6 +154,7 @@ namespace dpp {
 
 constexpr int kMaxPartialBlocks = 4096;
 constexpr int kMaxDotWidth = 40;   // >= gmres restart + 2
+constexpr int kMaxGmresRestart = 30;   // Givens / Hessenberg state of the device-resident GMRES (krylov.cu)
 constexpr int kNumScalars = 256;
 
 // Number of x-segments for the plane-streaming kernels: CTAs are (tile, segment) items dispatched by the
@@ -248,6 +250,8 @@ void comm_destroy(dpp_context* ctx);
 // ---- assemble_csr.cu
 int csr_assemble(dpp_context* ctx, int64_t* nnz);
 int csr_export(dpp_context* ctx, int64_t* indptr, int32_t* indices, double* data);
+int csr_export_block(dpp_context* ctx, int fr, int fc, int64_t* indptr, int32_t* indices, double* data);
+int csr_time_phases(dpp_context* ctx, int reps, double* symbolic_ms, double* numeric_ms, int64_t* nnz);
 int csr_spmv(dpp_context* ctx, const double* x, double* y, double* dot_partials, int* n_partial_blocks,
              const double* skip_flag);
 void csr_invalidate(dpp_context* ctx);

@@ -458,7 +458,7 @@ int gmres_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, doubl
   const VecLayout L = layout(ctx, 2);
   const int64_t len = 2 * ctx->n_nodes;
   const int slot = 0;
-  restart = std::max(1, std::min(restart, 30));
+  restart = std::max(1, std::min(restart, kMaxGmresRestart));
   while ((int)K->V.size() < restart + 1) {
     double* v = nullptr;
     DPP_CHECK(dev_alloc(ctx, &v, len));
@@ -675,7 +675,7 @@ int gmres_run_device(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b
   const VecLayout L = layout(ctx, 2);
   const int64_t len = 2 * ctx->n_nodes;
   const int slot = 0;
-  restart = std::max(1, std::min(restart, 30));
+  restart = std::max(1, std::min(restart, kMaxGmresRestart));
   while ((int)K->V.size() < restart + 1) {
     double* v = nullptr;
     DPP_CHECK(dev_alloc(ctx, &v, len));
@@ -999,6 +999,12 @@ int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_r
   if (!ctx->have_params) {
     ctx->set_error("dpp_solve: call dpp_set_params first");
     return DPP_ERR_STATE;
+  }
+  if (opt->ksp_type == DPP_KSP_GMRES && (opt->gmres_restart < 1 || opt->gmres_restart > kMaxGmresRestart)) {
+    // the device-resident Hessenberg / Givens state is sized for restart <= 30 (PETSc's default): refuse
+    // rather than silently run GMRES(30) with different iteration counts than PETSc would report
+    ctx->set_error("ksp_gmres_restart must be in [1, " + std::to_string(kMaxGmresRestart) + "]");
+    return DPP_ERR_INVALID;
   }
   DPP_CHECK(ensure_work(ctx));
   Krylov* K = ctx->krylov;

@@ -182,9 +182,23 @@ class SlabComm:
         # and mailbox; the library falls back to NCCL by itself if any rank cannot take part
         if self._backend == "nccl":
             handle.comm_ipc_import(self.all_gather_bytes(handle.comm_ipc_export()))
-            modes = self.all_gather_bytes(bytes([handle.info().peer_memory]))
-            if len(set(modes)) != 1:   # every rank must run the same protocol
-                handle.comm_ipc_disable()
+        self.agree_on_protocol(handle)
+
+    def agree_on_protocol(self, handle):
+        """Every rank must run the same reduction / halo protocol: peer memory or NCCL, fused two-kernel CG (two
+        reductions per iteration) or the unfused sequence (three), one kernel family.  Each is a rank-local fact
+        (IPC import result; uniform-grid test of the rank's own slab), so the ranks compare and settle on the
+        common denominator instead of hanging in mismatched collectives."""
+        info = handle.info()
+        mine = bytes([info.peer_memory & 0xFF, 1 if handle.fused_cg_supported() else 0, info.kernel_family & 0xFF])
+        votes = self.all_gather_bytes(mine)
+        if len({v[0] for v in votes}) != 1:
+            handle.comm_ipc_disable()
+        if len({v[1] for v in votes}) != 1:
+            handle.set_fused_cg(False)
+        if len({v[2] for v in votes}) != 1:
+            raise RuntimeError(f"slab ranks disagree on the kernel family {[v[2] for v in votes]}: the mesh must be "
+                               "structured on every rank or on none")
 
     def destroy(self):
         if self._dist is not None and self._dist.is_initialized():

@@ -60,8 +60,14 @@ def normalise_local_order(cnm: np.ndarray, node_coords: np.ndarray) -> np.ndarra
     return out
 
 
+def is_mixed(W) -> bool:
+    return hasattr(W, "num_sub_spaces") and W.num_sub_spaces() == 2
+
+
 def space_data(W) -> SpaceData:
-    V = W.sub(0)
+    """W: the 2-field mixed space, or one scalar pressure space V (the per-scale systems of dpp_delayed_form,
+    forms/dpp.py:135-205, live on V; the handle then holds V x V and serves its diagonal blocks)."""
+    V = W.sub(0) if is_mixed(W) else W
     mesh = W.mesh()
     degree = _degree_of(V)
     dim = int(mesh.geometric_dimension())
@@ -85,14 +91,17 @@ def space_data(W) -> SpaceData:
     return SpaceData(dim, degree, n_nodes, cnm, coords, ccnm, getattr(mesh, "slab", None), node_coords)
 
 
-def bc_data(W, bcs) -> List[Tuple[int, np.ndarray, np.ndarray]]:
-    """[(field, nodes, values)] for each DirichletBC (later BCs on the same field override)."""
+def bc_data(W, bcs, scalar_field: Optional[int] = None) -> List[Tuple[int, np.ndarray, np.ndarray]]:
+    """[(field, nodes, values)] for each DirichletBC (later BCs on the same field override).  `scalar_field`:
+    the BCs live on a scalar space V (fd.DirichletBC(V, g, ...)) and constrain that field of V x V."""
     out = []
     for bc in bcs or []:
         Vb = bc.function_space()
         field = getattr(Vb, "index", None)
         if field is None:
-            raise ValueError("DirichletBC must be built on W.sub(i)")
+            if scalar_field is None:
+                raise ValueError("DirichletBC must be built on W.sub(i)")
+            field = scalar_field
         nodes = np.asarray(bc.nodes, dtype=np.int32)
         if hasattr(bc, "values"):
             vals = np.asarray(bc.values(), dtype=np.float64)

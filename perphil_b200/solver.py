@@ -18,7 +18,30 @@ from .backend import PINNED, DppHandle
 from .forms import dpp_form, dpp_splitted_form
 from .mesh import Function, MixedFunctionSpace
 from .parameters import B200_BACKEND, B200_BACKEND_KEY, DPPParameters
-from .provider import bc_data, space_data
+from .provider import bc_data, is_mixed, space_data
+
+
+class ConvergenceError(RuntimeError):
+    """The Krylov / Picard iteration stopped with a negative converged reason.  The reference's
+    ``solver.solve()`` (solvers/solver.py:71, :121: Firedrake Linear/NonlinearVariationalSolver) raises
+    ``firedrake.exceptions.ConvergenceError`` in that case; when Firedrake is importable this class derives
+    from it, so ``except ConvergenceError`` written against the reference keeps working."""
+
+    def __init__(self, message: str, reason: int = 0, iterations: int = 0, residual_norm: float = float("nan")):
+        super().__init__(message)
+        self.reason, self.iterations, self.residual_norm = int(reason), int(iterations), float(residual_norm)
+
+
+try:  # pragma: no cover - Firedrake is not installable here
+    from firedrake.exceptions import ConvergenceError as _FdConvergenceError
+
+    class ConvergenceError(ConvergenceError, _FdConvergenceError):  # type: ignore[no-redef]
+        pass
+except Exception:
+    pass
+
+_REASONS = {-3: "DIVERGED_MAX_IT", -4: "DIVERGED_DTOL", -5: "DIVERGED_BREAKDOWN", -9: "DIVERGED_NANORINF",
+            -10: "DIVERGED_INDEFINITE_MAT", -100: "DIVERGED_COMM_TIMEOUT"}
 
 
 @dataclass(frozen=True)
@@ -51,7 +74,7 @@ def handle_for(W, device: Optional[int] = None) -> DppHandle:
         h = DppHandle(sd.dim, sd.degree, sd.cell_node_map, sd.coords, sd.coord_cell_node_map, n_nodes=sd.n_nodes,
                       device=dev)
     if comm is not None and comm.size > 1:
-        comm.attach(h, sd, W.sub(0))
+        comm.attach(h, sd, W.sub(0) if is_mixed(W) else W)
     try:
         ref = weakref.ref(W, lambda _r, k=key: _drop(k))
     except TypeError:
@@ -106,8 +129,13 @@ def options_from_petsc(handle: DppHandle, params: Dict, nonlinear: bool = False)
     opt.operator_mode = L.OP_ASSEMBLED if mat_type == "aij" else L.OP_MATRIX_FREE
     if nonlinear or "snes_type" in params:
         st = params.get("snes_type", "picard_split")
-        if st not in ("picard_split", "ngs"):
-            raise NotImplementedError(f"snes_type={st!r}: only the block Picard (scale-splitting) iteration is built")
+        if st != "picard_split":
+            # PICARD_*_SOLVER_PARAMS (solvers/parameters.py:71-95) ask for PETSc's pointwise SNES NGS /
+            # nrichardson sweeps, whose iteration counts (92 / 5135 in the stored runs) a block method does not
+            # reproduce: refuse instead of silently answering with 6 block-Picard iterations
+            raise NotImplementedError(
+                f"snes_type={st!r} is not built for the B200 path; the scale-splitting block iteration is selected "
+                'with the explicit key "snes_type": "picard_split" (B200_PICARD_SPLIT_PARAMS)')
         opt.ksp_type = L.KSP_PICARD
         opt.rtol = float(params.get("snes_rtol", 1e-8))
         opt.atol = float(params.get("snes_atol", 1e-12))
@@ -125,11 +153,16 @@ def options_from_petsc(handle: DppHandle, params: Dict, nonlinear: bool = False)
     if pc not in _PC:
         raise NotImplementedError(f"pc_type={pc!r} is not built for the B200 path (available: {sorted(_PC)})")
     opt.ksp_type, opt.pc_type = _KSP[ksp], _PC[pc]
-    opt.rtol = float(params.get("ksp_rtol", 1e-5))     # PETSc defaults when unset
+    # unset keys: PETSc's defaults, except ksp_rtol, for which Firedrake's variational solvers inject 1e-7
+    # (solving_utils DEFAULT_KSP_PARAMETERS) -- what the reference's solve_dpp therefore runs with
+    opt.rtol = float(params.get("ksp_rtol", 1e-7))
     opt.atol = float(params.get("ksp_atol", 1e-50))
     opt.dtol = float(params.get("ksp_divtol", 1e4))
     opt.max_it = int(params.get("ksp_max_it", 10000))
     opt.gmres_restart = int(params.get("ksp_gmres_restart", 30))
+    if ksp == "gmres" and not 1 <= opt.gmres_restart <= 30:
+        raise NotImplementedError(f"ksp_gmres_restart={opt.gmres_restart}: the B200 GMRES keeps its Hessenberg / "
+                                  "Givens state for restart lengths 1..30 (PETSc's default is 30)")
     if pc == "fieldsplit":
         fs = params.get("pc_fieldsplit_type", "multiplicative")
         if fs not in ("additive", "multiplicative"):
@@ -164,13 +197,28 @@ def _new_function(W):
     return fd.Function(W)
 
 
-def _run(W, model_params, bcs, params, nonlinear, fields=None, monitor=None):
-    h = handle_for(W)
+def configure_handle(h: DppHandle, W, model_params, bcs) -> None:
+    """Upload DPPParameters and Dirichlet data (DppHandle skips uploads that repeat what it already holds, so
+    repeated solves of one problem keep the diagonal, the boundary classification and the CUDA graphs)."""
     h.set_params(float(model_params.k1), float(model_params.k2), float(model_params.beta), float(model_params.mu))
     got = {f: (n, v) for f, n, v in bc_data(W, bcs)}
     for f in (0, 1):
         n, v = got.get(f, (np.zeros(0, np.int32), np.zeros(0)))
         h.set_dirichlet(f, n, v)
+
+
+def _raise_if_diverged(info, what: str):
+    if info.converged_reason < 0:
+        name = _REASONS.get(int(info.converged_reason), "DIVERGED")
+        raise ConvergenceError(
+            f"{what} failed to converge after {info.iterations} iterations with reason: {name} "
+            f"({info.converged_reason}), residual norm {info.residual_norm:.6e}",
+            info.converged_reason, info.iterations, info.residual_norm)
+
+
+def _run(W, model_params, bcs, params, nonlinear, fields=None, monitor=None):
+    h = handle_for(W)
+    configure_handle(h, W, model_params, bcs)
     opt = options_from_petsc(h, params, nonlinear)
     hist_cap = int(params.get("b200_history", 0)) or (min(opt.max_it + 1, 1 << 16) if "ksp_monitor" in params else 0)
     n = h.n_nodes
@@ -187,6 +235,10 @@ def _run(W, model_params, bcs, params, nonlinear, fields=None, monitor=None):
         tag = "SNES Function norm" if nonlinear else "KSP Residual norm"
         for i, r in enumerate(info.history):
             print(f"  {i:3d} {tag} {r:.12e}")
+    _LAST_INFO[0] = info
+    if not params.get("b200_error_if_not_converged", True):
+        return sol, info
+    _raise_if_diverged(info, "Nonlinear solve" if nonlinear else "Linear solve")
     return sol, info
 
 

@@ -18,3 +18,10 @@ def pytest_configure(config):
 def golden():
     with open(os.path.join(ROOT, "tests", "golden", "reference_stored.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_large():
+    """Oracle pins at the BASELINE sizes (C oracle run once on the CPU; tests/golden/make_golden_large.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "large_sizes.json")) as f:
+        return json.load(f)

@@ -84,6 +84,34 @@ def test_darcy_velocity_unstructured_and_renumbered(cells, degree, distort):
     h.close()
 
 
+def test_darcy_velocity_converges_to_the_manufactured_velocities():
+    """Reference-derived check of the Darcy row: the projected velocity of the interpolated exact pressure converges
+    to u_i = -(k_i/mu) grad p_i of utils/manufactured_solutions.py:21-37 (2-D) and :72-81 (3-D); the GPU projection is
+    bitwise repeatable (ordered gather, no atomics)."""
+    prm = pb.DPPParameters(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
+    for dim, sizes in [(2, (16, 32, 64)), (3, (8, 16, 32))]:
+        errs = {0: [], 1: []}
+        for N in sizes:
+            mesh = pb.UnitSquareMesh(N, N) if dim == 2 else pb.UnitCubeMesh(N, N, N)
+            _, V = pb.create_function_spaces(mesh)
+            W = V * V
+            u1, p1, u2, p2 = pb.exact_expressions(mesh, prm)
+            u1e, p1e, u2e, p2e = pb.interpolate_exact(mesh, None, W.sub(0), prm)
+            assert u1e.dat.data.shape == (V.dim(), dim)
+            inner = np.ones(V.dim(), bool); inner[V.boundary_nodes] = False
+            for f, (pe, ue, k) in enumerate([(p1e, u1e, prm.k1), (p2e, u2e, prm.k2)]):
+                vel = pb.calculate_darcy_velocity_from_pressure(pe, k, rtol=1e-12)
+                again = pb.calculate_darcy_velocity_from_pressure(pe, k, rtol=1e-12)
+                assert np.array_equal(vel.dat.data, again.dat.data)
+                d = (vel.dat.data - ue.dat.data)[inner]
+                errs[f].append(np.sqrt(np.mean(d ** 2)) / np.sqrt(np.mean(ue.dat.data ** 2)))
+            pb.release_handles()
+        for f in (0, 1):
+            e = errs[f]
+            assert e[1] < e[0] / 2.0 and e[2] < e[1] / 2.0, (dim, f, e)
+            assert e[2] < (1e-2 if dim == 2 else 4e-2), (dim, f, e)
+
+
 @pytest.mark.parametrize("N", [4, 8, 12])
 def test_lanczos_condition_numbers_match_conditioning_3d_csv(golden, N):
     """kappa(A), kappa(A00), kappa(A11) of the 3-D hex Q1 system with manufactured BCs, as stored by the reference

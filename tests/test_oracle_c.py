@@ -77,3 +77,58 @@ def test_c_cg_thread_count_does_not_change_iterations():
     co.set_num_threads(n0)
     assert a.iteration_number == b.iteration_number
     assert np.linalg.norm(a.u - b.u) <= 1e-10 * np.linalg.norm(a.u)
+
+
+INNER = {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_atol": 1e-50, "ksp_max_it": 10000}
+
+
+@pytest.mark.parametrize("cells", [(8, 8, 8), (10, 10), (16, 16)])
+@pytest.mark.parametrize("pc", ["none", "jacobi", "fieldsplit", "fieldsplit_additive"])
+def test_c_gmres_matches_python_oracle(cells, pc):
+    """KSPGMRES(30) / PCFIELDSPLIT of the C oracle (used to pin BASELINE config 5 at 128^3) against the Python
+    oracle, which reproduces the reference's stored GMRES histories and counts 10/40/292 (test_oracle_golden)."""
+    osys, csys = _pair(cells, 1)
+    okw = {"none": dict(pc_type="none"), "jacobi": dict(pc_type="jacobi"),
+           "fieldsplit": dict(pc_type="fieldsplit", inner=INNER),
+           "fieldsplit_additive": dict(pc_type="fieldsplit", fieldsplit_type="additive", inner=INNER)}[pc]
+    ref = orc.solve_dpp_oracle(osys, "gmres", **okw)
+    got = csys.gmres(pc, inner=INNER, history=len(ref.history) + 8)
+    assert got.reason == ref.reason
+    assert abs(got.iteration_number - ref.iteration_number) <= max(2, ref.iteration_number // 30)
+    k = min(len(ref.history), len(got.history), 12)
+    assert np.allclose(got.history[:k], ref.history[:k], rtol=1e-8)
+    assert np.linalg.norm(got.u - ref.u) <= 1e-8 * np.linalg.norm(ref.u)
+    if cells == (16, 16) and pc == "none":
+        assert got.iteration_number == 292      # convergence.csv (README example size)
+
+
+def test_c_gmres_config5_matches_python_oracle():
+    kw = dict(k1=1.0, k2=1e-6, beta=1e2, mu=1.0)
+    osys = orc.build_system(orc.structured_mesh((8, 8, 8), 1), orc.Params(**kw), ("const", 1.0, 0.0))
+    csys = co.constant_bc_system((8, 8, 8), 1, **kw)
+    for pc, okw in [("none", dict(pc_type="none")), ("jacobi", dict(pc_type="jacobi")),
+                    ("fieldsplit", dict(pc_type="fieldsplit", inner=INNER))]:
+        ref = orc.solve_dpp_oracle(osys, "gmres", **okw)
+        got = csys.gmres(pc, inner=INNER)
+        assert abs(got.iteration_number - ref.iteration_number) <= 2
+        assert np.linalg.norm(got.u - ref.u) <= 1e-7 * np.linalg.norm(ref.u)
+    ref = orc.solve_dpp_oracle(osys, "cg", "jacobi")
+    assert csys.cg("jacobi").iteration_number == ref.iteration_number
+
+
+def test_large_size_pins_belong_to_the_systems_they_name(golden_large):
+    """tests/golden/large_sizes.json was produced by tests/golden/make_golden_large.py; the cheap part of each
+    record (system size, ||b||, the iteration-0 norm ||D^-1 b||) is recomputed here from a fresh build."""
+    for key, build, run in [("cfg3_128", lambda N: co.manufactured_system((N, N, N), 1), None),
+                            ("cfg5_128", lambda N: co.constant_bc_system((N, N, N), 1), "cg_jacobi")]:
+        pin = golden_large[key]
+        csys = build(pin["cells"])
+        assert (csys.n_dof, csys.nnz) == (pin["n_dof"], pin["nnz"])
+        b = csys.rhs()
+        assert np.linalg.norm(b) == pytest.approx(pin["rhs_norm2"], rel=1e-12)
+        rec = pin if run is None else pin["runs"][run]
+        first = csys.cg("jacobi", max_it=1, history=2)
+        assert first.history[0] == pytest.approx(rec["history"][0], rel=1e-12)
+        csys.close()
+    pin = golden_large["cfg3_256"]
+    assert pin["iterations"] == 387 and pin["n_dof"] == 2 * 257 ** 3 and pin["nnz"] == 4 * (3 * 256 + 1) ** 3
