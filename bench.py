@@ -152,6 +152,71 @@ def cpu_baseline(N, repeats=1, single_thread_size=64):
             "cpu_model": cpu_model(), "single_thread": one}
 
 
+def general_kernel_entry(N, peak, peak_kind):
+    """Second roofline entry: the element-based matrix-free apply (csrc/apply_cells.cu) on a GENERAL mesh -- the
+    N^3 hex Q1 lattice with perturbed interior vertices (non-affine cells), randomly permuted node numbering and
+    cell order -- against the unstructured bytes model of SURVEY 8(d): 58 B/node + 32 B/cell.  The kernel is bound
+    by the fp64 FMA pipe, not by HBM (~1260 fp64 instructions per distorted cell), so the fraction
+    of the fp64 issue rate (64 lanes/clk/SM at the sampled SM clock) is reported next to the HBM fraction."""
+    from perphil_b200.backend import DppHandle
+    from tools.general_mesh import shuffled_distorted_hex
+
+    t0 = time.perf_counter()
+    cnm, X, bn = shuffled_distorted_hex(N, 0.25, seed=1)
+    h = DppHandle.from_mesh_arrays(3, 1, cnm, X, X, cnm, n_nodes=X.shape[0])
+    h.set_params(1.0, 1e-2, 1.0, 1.0)
+    g = np.random.default_rng(2).standard_normal(bn.size)
+    h.set_dirichlet(0, bn, g)
+    h.set_dirichlet(1, bn, -g)
+    h.time_apply(reps=1, warmup=0, with_dot=True)          # one-time cell-block setup (host) + first launch
+    setup_s = time.perf_counter() - t0
+    ms = h.time_apply(reps=20, warmup=3, with_dot=True)
+    u, info = h.solve()                                    # Jacobi-CG (unfused kernel sequence) on the same mesh
+    nn, ncell = X.shape[0], cnm.shape[0]
+    bytes_model = 58 * nn + 32 * ncell
+    fam = h.info().kernel_family
+    sm = h.info().sm_count
+    h.close()
+    fp64_rate = sm * 64 * 1.9e9
+    return {"bound": "fp64", "kernel": "k_cells_stage + k_cells_q1<2> + k_cells_gather<2> (general hex Q1, distorted + shuffled)",
+            "workload": f"{N}^3 hex Q1, vertices perturbed by 0.25 h, random node/cell numbering ({2 * nn} DoF)",
+            "kernel_family": "general" if fam == 0 else "structured",
+            "ms_per_apply": ms, "matvec_gdofs": 2 * nn / ms / 1e6,
+            "achieved": bytes_model / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": bytes_model / ms / 1e6 / peak,
+            "peak_kind": peak_kind, "bytes_model": "58 B/node + 32 B/cell (SURVEY 8d, unstructured data model)",
+            "algorithmic_bytes": bytes_model, "traffic": None,
+            "fp64_instructions_model": 1260 * ncell, "fp64_pipe_frac_at_1.9GHz": 1260 * ncell / (ms * 1e-3) / fp64_rate,
+            "solve": {"ksp": "cg", "pc": "jacobi", "iterations": int(info.iterations), "solve_ms": info.solve_ms,
+                      "gdofs": 2 * nn * info.iterations / info.solve_ms / 1e6},
+            "first_call_s": setup_s}
+
+
+def assembly_entry(N, peak):
+    """CSR assembly of the 2x2-block matrix (BASELINE configs[1] top size by default): symbolic and numeric phase
+    separately (CUDA events), numeric against the nnz * 12 B model (8 B value written + 4 B column index)."""
+    import perphil_b200 as pb
+
+    mesh = pb.UnitCubeMesh(N, N, N)
+    _, V = pb.create_function_spaces(mesh)
+    W = V * V
+    prm = pb.DPPParameters(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
+    _, p1, _, p2 = pb.exact_expressions_3d(mesh, prm)
+    bcs = [pb.DirichletBC(W.sub(0), p1, "on_boundary"), pb.DirichletBC(W.sub(1), p2, "on_boundary")]
+    from perphil_b200.solver import configure_handle
+
+    h = pb.handle_for(W)
+    configure_handle(h, W, prm, bcs)
+    sym_ms, num_ms, nnz = h.time_assembly(reps=5)
+    spmv_ms = h.time_apply(reps=10, warmup=2, assembled=True)
+    ndof = 2 * h.n_nodes
+    out = {"workload": f"{N}^3 hex Q1, nnz {nnz}", "symbolic_ms": sym_ms, "numeric_ms": num_ms,
+           "numeric_gbs": 12 * nnz / num_ms / 1e6, "numeric_frac": 12 * nnz / num_ms / 1e6 / peak,
+           "bytes_model": "nnz * 12 B", "spmv_ms": spmv_ms, "spmv_gbs": (12 * nnz + 24 * ndof) / spmv_ms / 1e6,
+           "spmv_frac": (12 * nnz + 24 * ndof) / spmv_ms / 1e6 / peak}
+    pb.release_handles()
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path for this metric.  perphil itself is Python glue over
     Firedrake/PETSc, which cannot be installed here or on the GPU box, so the arm times the
@@ -197,6 +262,9 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=96,
                     help="cells per direction of the bounded CPU sample (cpu_baseline AND --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--general-size", type=int, default=128,
+                    help="cells per direction of the shuffled + distorted mesh of the general-kernel entry (0: skip)")
+    ap.add_argument("--assembly-size", type=int, default=128, help="CSR assembly timing entry (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -344,6 +412,10 @@ def main():
         "solve_roofline": {"achieved": solve_gbs, "peak": peak, "unit": "GB/s", "frac": solve_gbs / peak,
                            "bytes_per_iteration": iter_bytes},
     }
+    if world == 1 and args.general_size > 0:
+        line["roofline_general"] = general_kernel_entry(args.general_size, peak, peak_kind)
+    if world == 1 and args.assembly_size > 0:
+        line["assembly"] = assembly_entry(args.assembly_size, peak)
     if not args.no_cpu and world == 1:   # reported on rank 0 at N=1 only
         line["cpu_baseline"] = cpu_baseline(args.cpu_size)
     print(json.dumps(line))

@@ -62,14 +62,32 @@ class DppHandle:
         (perphil_b200.lattice) it is created on the lexicographically re-numbered mesh, so that the
         structured kernels serve it, and the numbering map is registered: every method of this class keeps
         speaking the caller's numbering."""
-        from .lattice import detect_lattice
+        from .lattice import detect_lattice, morton_permutation
 
         lat = detect_lattice(dim, degree, cell_node_map, node_coords, vertex_coords, coord_cell_node_map) if renumber else None
-        if lat is None or lat.is_identity:
+        if lat is not None:
+            if lat.is_identity:
+                return cls(dim, degree, cell_node_map, vertex_coords, coord_cell_node_map, n_nodes=n_nodes, device=device)
+            h = cls(dim, degree, lat.cell_node_map, lat.vertex_coords, lat.cell_vertex_map, n_nodes=lat.perm.size,
+                    device=device)
+            h.set_numbering(lat.perm)
+            return h
+        if not renumber:
             return cls(dim, degree, cell_node_map, vertex_coords, coord_cell_node_map, n_nodes=n_nodes, device=device)
-        h = cls(dim, degree, lat.cell_node_map, lat.vertex_coords, lat.cell_vertex_map, n_nodes=lat.perm.size,
-                device=device)
-        h.set_numbering(lat.perm)
+        # not a tensor grid: the general (element-based) kernels.  Re-number nodes and vertices along a Morton
+        # curve so that the node list of every cell block is a few contiguous ranges (coalesced gathers)
+        cnm = np.asarray(cell_node_map)
+        ccnm = cnm if coord_cell_node_map is None else np.asarray(coord_cell_node_map)
+        perm = morton_permutation(node_coords)
+        same = ccnm is cnm or (ccnm.shape == cnm.shape and np.asarray(vertex_coords).shape[0] == perm.size
+                               and np.array_equal(ccnm, cnm))
+        vperm = perm if same else morton_permutation(vertex_coords)
+        vx = np.empty_like(np.asarray(vertex_coords, dtype=np.float64))
+        vx[vperm] = np.asarray(vertex_coords, dtype=np.float64)
+        new_cnm = np.ascontiguousarray(perm[cnm], dtype=np.int32)
+        new_ccnm = new_cnm if same else np.ascontiguousarray(vperm[ccnm], dtype=np.int32)
+        h = cls(dim, degree, new_cnm, vx, new_ccnm, n_nodes=perm.size, device=device)
+        h.set_numbering(perm)
         return h
 
     def set_numbering(self, user_to_internal: np.ndarray):

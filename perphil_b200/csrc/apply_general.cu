@@ -13,6 +13,7 @@
 // family (apply_structured.cu) is the fast path for tensor grids, this family is the general one.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "dpp_internal.cuh"
@@ -300,6 +301,12 @@ int general_apply(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks) {
   if (!ctx->general_ready) {
     ctx->set_error("general kernel family not set up");
     return DPP_ERR_STATE;
+  }
+  // Q1 hexahedra on a whole (unpartitioned) mesh: the element-based cell-block kernel (apply_cells.cu); the
+  // row-owner gather below serves 2-D / Q2 meshes (DPP_GENERAL_ROW_OWNER=1 forces it: parity tests compare both)
+  if (cells_supported(ctx) && a.owned_begin == 0 && a.owned_end == ctx->n_nodes && getenv("DPP_GENERAL_ROW_OWNER") == nullptr) {
+    DPP_CHECK(cells_setup(ctx));
+    return cells_apply(ctx, a, n_partial_blocks);
   }
   GenArgs g{};
   fill_common(ctx, g);

@@ -188,6 +188,7 @@ void dpp_destroy(dpp_handle ctx) {
   dpp::krylov_destroy(ctx);
   dpp::cg_fused_destroy(ctx);
   dpp::csr_destroy(ctx);
+  dpp::cells_destroy(ctx);
   dpp::comm_destroy(ctx);
   void* ptrs[] = {ctx->d_cnm, ctx->d_coords, ctx->ccnm_alias ? nullptr : ctx->d_ccnm, ctx->d_tables, ctx->d_adj_ptr,
                   ctx->d_adj_cell, ctx->d_adj_loc, ctx->d_cell_geom, ctx->d_mask, ctx->d_g, ctx->d_solution, ctx->d_diag,

@@ -64,6 +64,7 @@ struct Krylov;  // krylov.cu
 struct FusedState;  // cg_fused_uniform.cu
 struct CsrMatrix;
 struct Comm;
+struct CellBlocks;  // apply_cells.cu
 
 }  // namespace dpp
 
@@ -105,6 +106,7 @@ struct dpp_context {
   uint8_t* d_adj_loc = nullptr;
   double* d_cell_geom = nullptr;  // [n_cells*8]: affine metric (6) + detJ + flag
   bool general_ready = false;
+  dpp::CellBlocks* cells = nullptr;   // cell-block decomposition of the element-based Q1 hex kernel (apply_cells.cu)
 
   // parameters
   bool have_params = false;
@@ -194,6 +196,14 @@ int structured_fix_rows(dpp_context* ctx, int nf, const int* fld, double* const*
 int general_setup(dpp_context* ctx, const int32_t* cnm_host);
 int general_apply(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks);
 int general_diagonal(dpp_context* ctx, const Coef& c, double* d_diag);
+
+// ---- apply_cells.cu: element-based kernel for general Q1 hexahedral meshes
+bool cells_supported(const dpp_context* ctx);
+bool cells_ready(const dpp_context* ctx);
+int cells_setup(dpp_context* ctx);
+int cells_apply(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks);
+int cells_stats(const dpp_context* ctx, int64_t* n_blocks, int64_t* total_slots, int64_t* affine_cells);
+void cells_destroy(dpp_context* ctx);
 
 // ---- operator.cu : dispatch + DPP coefficient blocks
 Coef dpp_coef(const dpp_context* ctx);                    // monolithic 2x2

@@ -95,3 +95,35 @@ def detect_lattice(dim: int, degree: int, cell_node_map: np.ndarray, node_coords
     grid = np.meshgrid(*vaxes, indexing="ij")
     vcoords = np.stack([g.ravel() for g in grid], axis=1)
     return Lattice(lex.astype(np.int32), cells, vaxes, ref_map, vcoords, _cell_map(cells, 1))
+
+
+def _spread21(v: np.ndarray) -> np.ndarray:
+    v = v.astype(np.uint64) & np.uint64(0x1FFFFF)
+    v = (v | (v << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+    v = (v | (v << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+    return v
+
+
+def morton_permutation(coords: np.ndarray) -> np.ndarray:
+    """int32 [n]: node id -> position along a Morton (Z-order) curve through the node coordinates.
+
+    Used for meshes that are NOT tensor grids: the element-based kernels stage each block of cells in shared
+    memory through that block's sorted node list, so nodes that are close in space should be close in memory
+    (Firedrake's own DMPlex/RCM numbering has some locality; a renumbering along the curve gives every cell block a
+    few contiguous index ranges whatever numbering the mesh came with).  The map is registered with
+    `dpp_set_numbering`, so callers keep their own numbering."""
+    X = np.asarray(coords, dtype=np.float64)
+    lo, hi = X.min(axis=0), X.max(axis=0)
+    scale = np.where(hi > lo, 2097151.0 / np.where(hi > lo, hi - lo, 1.0), 0.0)
+    q = ((X - lo) * scale).astype(np.uint64)
+    dim = X.shape[1]
+    key = np.zeros(X.shape[0], dtype=np.uint64)
+    for d in range(dim):
+        key |= _spread21(q[:, d]) << np.uint64(dim - 1 - d)
+    order = np.argsort(key, kind="stable")          # position -> node
+    perm = np.empty(X.shape[0], dtype=np.int32)
+    perm[order] = np.arange(X.shape[0], dtype=np.int32)
+    return perm
