@@ -35,6 +35,7 @@ struct CsrMatrix {
   int64_t* indptr = nullptr;  // [2n+1]
   int32_t* indices = nullptr; // [4 nnz_g]
   double* data = nullptr;     // [4 nnz_g]
+  double* tabs = nullptr;     // [7][729] reference-cell integrals (6 stiffness tables + mass) for the numeric kernel
   bool numeric_valid = false;
 };
 
@@ -207,6 +208,7 @@ struct NumArgs {
   const int64_t* g_ptr;
   const int32_t* g_cols;
   const uint8_t* mask;  // [2n]
+  const double* tabs;   // [7][729] reference-cell integrals in global memory
   long long n, nnz_g;
   Coef c;
   double* data;
@@ -225,6 +227,14 @@ __global__ void __launch_bounds__(NUM_THREADS) k_numeric(const NumArgs g) {
   constexpr int NQ = P1, NV = 1 << DIM, NQP = NPC;   // (P+1)^dim Gauss points = one per lane b < NPC
   __shared__ double sK[ROWS][MAXROW], sM[ROWS][MAXROW];
   __shared__ double sG[ROWS][NQP][7];        // metric at the Gauss points of the current (non-affine) cell
+  // reference-cell integrals: constant memory serialises the per-lane addresses (a * NPC + lane), so the tables
+  // the affine path reads are staged in shared memory (NPC <= 9) or read through the read-only path (Q2 hex)
+  constexpr bool TAB_SMEM = NPC <= 9;
+  __shared__ double sT[TAB_SMEM ? 7 * NPC * NPC : 1];
+  if (TAB_SMEM) {
+    for (int i = threadIdx.x; i < 7 * NPC * NPC; i += NUM_THREADS) sT[i] = g.tabs[(i / (NPC * NPC)) * 729 + i % (NPC * NPC)];
+    __syncthreads();
+  }
   const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
   const long long r = (long long)blockIdx.x * ROWS + grp;
   // the lanes of one group live in one warp: group-wide synchronisation = __syncwarp on the group's mask
@@ -245,8 +255,8 @@ __global__ void __launch_bounds__(NUM_THREADS) k_numeric(const NumArgs g) {
       if (lane < NPC) {
         const int ab = a * NPC + lane;
 #pragma unroll
-        for (int s = 0; s < 6; ++s) kab = fma(gm[s], cTK[s * 729 + ab], kab);
-        mab = gm[6] * cTM[ab];
+        for (int s = 0; s < 6; ++s) kab = fma(gm[s], TAB_SMEM ? sT[s * NPC * NPC + ab] : __ldg(g.tabs + s * 729 + ab), kab);
+        mab = gm[6] * (TAB_SMEM ? sT[6 * NPC * NPC + ab] : __ldg(g.tabs + 6 * 729 + ab));
       }
     } else {             // general cell: Gauss quadrature of the multilinear map
       if (lane < NQP) {  // lane = Gauss point (q0, q1, q2) = (b0, b1, b2)
@@ -419,6 +429,11 @@ int upload_reference_tables(dpp_context* ctx) {
     }
   DPP_CUDA(cudaMemcpyToSymbol(cTK, TK.data(), sizeof(double) * 6 * 729));
   DPP_CUDA(cudaMemcpyToSymbol(cTM, TM.data(), sizeof(double) * 729));
+  if (ctx->csr) {
+    if (!ctx->csr->tabs) DPP_CHECK(dev_alloc(ctx, &ctx->csr->tabs, 7 * 729));
+    DPP_CUDA(cudaMemcpy(ctx->csr->tabs, TK.data(), sizeof(double) * 6 * 729, cudaMemcpyHostToDevice));
+    DPP_CUDA(cudaMemcpy(ctx->csr->tabs + 6 * 729, TM.data(), sizeof(double) * 729, cudaMemcpyHostToDevice));
+  }
   return fe_upload_tables(ctx);
 }
 
@@ -497,7 +512,7 @@ int numeric(dpp_context* ctx, CsrMatrix* A) {
   NumArgs g{};
   g.adj_ptr = ctx->d_adj_ptr; g.adj_cell = ctx->d_adj_cell; g.adj_loc = ctx->d_adj_loc;
   g.cnm = ctx->d_cnm; g.ccnm = ctx->d_ccnm; g.coords = ctx->d_coords; g.geom = ctx->d_cell_geom;
-  g.pos = A->pos; g.g_ptr = A->g_ptr; g.g_cols = A->g_cols; g.mask = ctx->d_mask;
+  g.pos = A->pos; g.g_ptr = A->g_ptr; g.g_cols = A->g_cols; g.mask = ctx->d_mask; g.tabs = A->tabs;
   g.n = ctx->n_nodes; g.nnz_g = A->nnz_g; g.c = dpp_coef(ctx); g.data = A->data;
   const int dim = ctx->dim, p = ctx->degree;
   const int npc = ctx->npc;
@@ -635,7 +650,7 @@ void csr_invalidate(dpp_context* ctx) {
 void csr_destroy(dpp_context* ctx) {
   CsrMatrix* A = ctx->csr;
   if (!A) return;
-  void* p[] = {A->g_ptr, A->g_cols, A->pos, A->indptr, A->indices, A->data};
+  void* p[] = {A->g_ptr, A->g_cols, A->pos, A->indptr, A->indices, A->data, A->tabs};
   for (void* q : p)
     if (q) cudaFree(q);
   delete A;

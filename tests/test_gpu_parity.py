@@ -604,6 +604,32 @@ def test_apply_structured_q2(cells, bc):
     assert rel_err(h.apply(x), ys) < APPLY_TOL
 
 
+@pytest.mark.parametrize("cells", [(20, 17, 33), (3, 4, 5), (2, 1, 1), (40, 9), (7, 70)])
+def test_q2_uniform_kernel_equals_table_kernel_and_oracle(cells, monkeypatch):
+    """The uniform-grid Q2 kernel (node pairs, 16-byte shared-memory loads, constant rows) against the table-driven
+    kernel on ragged tile sizes, and against the oracle where it reaches; nf = 1 blocks through the Picard solve."""
+    W, p, bcs, osys = make_problem(cells, 2) if int(np.prod(cells)) <= 400 else (make_problem(cells, 2)[:3] + (None,))
+    h = configured_handle(W, p, bcs)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(2 * h.n_nodes)
+    monkeypatch.delenv("DPP_Q2_TABLE_KERNEL", raising=False)
+    y = h.apply(x)
+    assert np.array_equal(y, h.apply(x))
+    monkeypatch.setenv("DPP_Q2_TABLE_KERNEL", "1")
+    y_tab = h.apply(x)
+    monkeypatch.delenv("DPP_Q2_TABLE_KERNEL", raising=False)
+    assert rel_err(y, y_tab) < APPLY_TOL
+    if osys is not None:
+        assert rel_err(y, osys.A_bc @ x) < APPLY_TOL
+    # unconstrained operator too (boundary rows computed, not replaced)
+    h.set_dirichlet(0, [], []); h.set_dirichlet(1, [], [])
+    y0 = h.apply(x)
+    monkeypatch.setenv("DPP_Q2_TABLE_KERNEL", "1")
+    assert rel_err(y0, h.apply(x)) < APPLY_TOL
+    monkeypatch.delenv("DPP_Q2_TABLE_KERNEL", raising=False)
+    pb.release_handles()
+
+
 def test_q2_diagonal_and_block_operators():
     W, p, bcs, osys = make_problem((4, 5, 3), 2)
     h = configured_handle(W, p, bcs)

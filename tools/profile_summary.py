@@ -57,7 +57,7 @@ KEYS = OrderedDict([
 ])
 
 
-def kernels(rep, out_md, out_json):
+def kernels(rep, out_md, out_json, what=None):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -65,8 +65,9 @@ def kernels(rep, out_md, out_json):
     summary = OrderedDict()
     with open(out_md, "w") as f:
         f.write(f"# ncu --set full capture ({rep.split('/')[-1]})\n\n")
-        f.write("`ncu --set full --clock-control none --import-source on` on `python bench.py --steps 1 --warmup 1 --no-cpu`"
-                " (256^3 hex Q1, Jacobi-CG). One row per captured launch.\n\n")
+        f.write("`ncu --set full --clock-control none --import-source on` on "
+                + (what or "`python bench.py --steps 1 --warmup 1 --no-cpu` (256^3 hex Q1, Jacobi-CG)")
+                + ". One row per captured launch.\n\n")
         cols = list(KEYS.values())
         f.write("| kernel | " + " | ".join(cols) + " | top stalls (per issue) |\n|---|" + "---:|" * len(cols) + "---|\n")
         for r in rows[2:]:
@@ -112,4 +113,4 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
     else:
-        kernels(sys.argv[2], sys.argv[3], sys.argv[4])
+        kernels(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else None)
