@@ -38,7 +38,13 @@ __device__ __forceinline__ double block_sum(double v, double* sm /*[VT/32]*/) {
 // (written); R: where the slot's PREVIOUS state is read from -- the slot itself, or a shared-memory snapshot the
 // kernel took in its prologue (S changes only in these epilogues, stream-ordered, so the snapshot is current;
 // reading it saves two dependent L2 round trips on the critical path of every iteration).
-__device__ __forceinline__ void apply_post(double* S, double* hist, int post, const double* R, double t0, double t1) {
+// Deferred x update (cg_fused_uniform.cu): the search directions of the last kXRing = 16 iterations stay in a ring of
+// buffers, their step lengths in `xring` ([kXRing] alpha, [kXRing] iteration tag); x += alpha_k p_k is applied for
+// kXRing - 1 iterations at a time by the r-update kernel (in iteration order: bitwise the x of KSPCG).
+constexpr int kXRing = 16;
+
+__device__ __forceinline__ void apply_post(double* S, double* hist, int post, const double* R, double t0, double t1,
+                                           double* xring = nullptr) {
   if (post == POST_CG_PAP) {
     if (R[S_REASON] != 0.0) return;  // the apply was a no-op: partials are stale
     const double pap = t0;
@@ -47,8 +53,14 @@ __device__ __forceinline__ void apply_post(double* S, double* hist, int post, co
       S[S_REASON] = (pap == pap) ? DPP_DIVERGED_INDEFINITE_MAT : DPP_DIVERGED_NANORINF;
       S[S_XPEND] = 0.0;
     } else {
-      S[S_ALPHA] = R[S_RZ] / pap;
+      const double alpha = R[S_RZ] / pap;
+      S[S_ALPHA] = alpha;
       S[S_XPEND] = 1.0;
+      if (xring != nullptr) {   // direction p_k of iteration k = its lives in ring buffer (k + 1) % kXRing
+        const int k = (int)R[S_ITS], j = (k + 1) % kXRing;
+        xring[j] = alpha;
+        xring[kXRing + j] = (double)k;
+      }
     }
     return;
   }
@@ -115,7 +127,8 @@ struct FoldPre {                  // shared-memory snapshot taken after griddepc
 // sm: kFinishSmem doubles of shared memory.
 __device__ __forceinline__ void finish_reduction(const double* __restrict__ partials, int nblocks, int width, double* S,
                                                  double* hist, int post, int out_offset, const IpcReduce& ipc,
-                                                 double* sm, bool sys_release = true, FoldPre pre = FoldPre{nullptr, nullptr}) {
+                                                 double* sm, bool sys_release = true, FoldPre pre = FoldPre{nullptr, nullptr},
+                                                 double* xring = nullptr) {
   double* vals = sm + VT / 32;
   volatile int* timed_out = reinterpret_cast<volatile int*>(sm + VT / 32 + kMboxEntry);
   double* recv = sm + VT / 32 + kMboxEntry + 2;   // [world][kMboxEntry - 1]
@@ -224,7 +237,7 @@ __device__ __forceinline__ void finish_reduction(const double* __restrict__ part
         S[S_TMP + out_offset + w] = t;
         if (w < 2) tw[w] = t;
       }
-      if (out_offset == 0) apply_post(S, hist, post, pre.S != nullptr ? pre.S : S, tw[0], tw[1]);
+      if (out_offset == 0) apply_post(S, hist, post, pre.S != nullptr ? pre.S : S, tw[0], tw[1], xring);
       else apply_post(S, hist, post);
     }
   }

@@ -7,6 +7,12 @@
 //                     iteration is deferred into it: p_old is on chip anyway]
 //   k_cg_r_update     reads r, w (2)          writes r (1)                  [z = D^-1 r only in registers]
 // = 9 passes per iteration instead of 13 for the unfused sequence (apply 2 + xr-update 7 + p-update 4).
+// Deferred x update (default; DPP_NO_DEFER_X=1 restores the scheme above): x is not touched every iteration.
+// The directions p_k go round a ring of kXRing = 16 buffers, their step lengths alpha_k into a small device
+// ring; every 15th iteration the r-update kernel adds the last fifteen alpha_k p_k to x, in iteration order
+// (bitwise the x of KSPCG).  The apply kernel then moves r, p_old in and p, w out (4 passes), x costs
+// (15 + 2) / 15 = 1.13 passes per iteration instead of 2: 8.13 passes per iteration; the ring takes 16 x 575 MB
+// of the 180 GB of HBM at 256^3.
 // The reciprocal diagonal is never read from memory: on a uniform grid diag(A) takes one of 8 values
 // per field (node on the domain boundary of axis x/y/z or not), kept in a 16-entry table.
 //
@@ -65,6 +71,7 @@ struct FArgs {
   const double* S;           // scalar slot of the solver (null in plain-apply mode)
   const double* dtab;        // [2][8] reciprocal diagonal per boundary class bx*4 + by*2 + bz
   int dom_lo, dom_hi;        // local plane 0 / n[0]-1 lies on the domain boundary (else it is a ghost plane)
+  int defer_x;               // x is updated by the r-update kernel from the direction ring, not here
   FoldArgs fold;             // <p,Ap> reduction epilogue run by the last CTA
 };
 
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
   bool xpend = false;
   if (FUSED) {
     beta = (s.S[S_ITS] == 0.0) ? 0.0 : s.S[S_RZ] / s.S[S_RZ_OLD];
-    xpend = s.S[S_XPEND] != 0.0;
+    xpend = !s.defer_x && s.S[S_XPEND] != 0.0;
     alpha_prev = xpend ? s.S[S_ALPHA] : 0.0;
   }
   double dot = 0.0;
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     }
     if (FUSED && s.fold.enabled && last_block_arrives(s.fold.counter, gridDim.x, &sm.last_flag))
       finish_reduction(s.dot_partials, (int)gridDim.x, 1, s.fold.S, s.fold.hist, s.fold.post, 0, s.fold.ipc, sm.fin,
-                       s.fold.ipc.ll == 3, FoldPre{sm.spre, &sm.seq_pre});
+                       s.fold.ipc.ll == 3, FoldPre{sm.spre, &sm.seq_pre}, s.fold.xring);
   }
 }
 
@@ -417,6 +424,10 @@ struct RArgs {
   int zero_class[2];         // field f: every domain-boundary node is a Dirichlet node (and no other)
   FoldArgs fold;
   IpcHalo halo;              // peer residual vectors: boundary planes are stored there as well
+  int defer_x;               // deferred x update: every (kXRing - 1)-th iteration x += sum alpha_k p_k from the ring
+  double* x;
+  const double* pr[kXRing];  // direction ring (padded, field-blocked)
+  const double* xring;       // [kXRing] alpha, [kXRing] iteration tag
 };
 
 constexpr int UNROLL = 4;   // pairs of nodes per thread and loop trip: 2 arrays x 4 x 16 B = 128 B in flight per thread
@@ -536,6 +547,39 @@ __global__ void __launch_bounds__(VT, 3) k_cg_r_update(const RArgs a) {
         INIT ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(wf + q));
     advance();
   }
+  if (!INIT && a.defer_x) {
+    // iteration k = its (this kernel's epilogue makes it k + 1): after every (kXRing - 1)-th iteration the fifteen
+    // directions p_{k-14} .. p_k are added to x in iteration order.  S[S_ITS] is written only by the last block's
+    // epilogue, after every block has arrived, so all blocks read the same k here.
+    const int k = (int)a.S[S_ITS];
+    if ((k + 1) % (kXRing - 1) == 0) {
+      constexpr int NDIR = kXRing - 1, CH = 8;     // directions per accumulate; loads in flight per chunk
+      double* xf = a.x + (long long)f * a.field;
+      const long long foff = (long long)f * a.field;
+      for (long long qq = a.ob + b + 2 * threadIdx.x; qq < qe; qq += 2 * VT) {
+        double2 xv = *reinterpret_cast<const double2*>(xf + qq);
+#pragma unroll
+        for (int c0 = 0; c0 < NDIR; c0 += CH) {
+          double2 pv[CH];
+          double al[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (c0 + j < NDIR) {
+              const int slot = (k - (NDIR - 1) + c0 + j + 1) % kXRing;
+              al[j] = a.xring[slot];
+              pv[j] = *reinterpret_cast<const double2*>(a.pr[slot] + foff + qq);
+            }
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (c0 + j < NDIR) {
+              xv.x = fma(al[j], pv[j].x, xv.x);
+              xv.y = fma(al[j], pv[j].y, xv.y);
+            }
+        }
+        *reinterpret_cast<double2*>(xf + qq) = xv;
+      }
+    }
+  }
   const double t0 = block_sum(srz, sm);
   const double t1 = block_sum(szz, sm);
   if (threadIdx.x == 0) {
@@ -597,6 +641,30 @@ __global__ void __launch_bounds__(VT) k_cg_x_finalize(PadGeom g, const double* _
     const unsigned k = (unsigned)n - row * g.nk;
     const long long q = f * g.field + (long long)row * g.pitch + k;
     x[f * g.n_nodes + n] = fma(alpha, pp[q], xp[q]);
+  }
+}
+
+// deferred x update: x_unpadded = x_padded + the step lengths times directions not yet added (iterations
+// floor(its / 15) * 15 .. its - 1, in iteration order)
+struct RingPtrs {
+  const double* p[kXRing];
+};
+__global__ void __launch_bounds__(VT) k_cg_x_finalize_ring(PadGeom g, const double* __restrict__ xp, RingPtrs pr,
+                                                            const double* __restrict__ S, const double* __restrict__ xring,
+                                                            long long ob, long long oe, double* __restrict__ x) {
+  const int its = (int)S[S_ITS];
+  const int lo = (its / (kXRing - 1)) * (kXRing - 1);
+  const int f = blockIdx.y;
+  for (long long n = ob + (long long)blockIdx.x * VT + threadIdx.x; n < oe; n += (long long)gridDim.x * VT) {
+    const unsigned row = (unsigned)(((unsigned long long)(unsigned)n * g.mag_k) >> g.sh_k);
+    const unsigned k = (unsigned)n - row * g.nk;
+    const long long q = f * g.field + (long long)row * g.pitch + k;
+    double v = xp[q];
+    for (int kk = lo; kk < its; ++kk) {
+      const int slot = (kk + 1) % kXRing;
+      v = fma(xring[slot], pr.p[slot][q], v);
+    }
+    x[f * g.n_nodes + n] = v;
   }
 }
 
@@ -713,6 +781,12 @@ struct FusedState {
   int bc_full_dom[2] = {-1, -1};  // dom_lo + 2*dom_hi the classification was made for
   unsigned long long* d_count = nullptr;
   bool attr_set = false;
+  // deferred x update: ring of direction buffers (pring[0], pring[1] alias buf[1], buf[2]) + their tensor maps
+  double* pring[kXRing] = {};
+  CUtensorMap tmr[2][kXRing];
+  double* d_xring = nullptr;      // [2 * kXRing]: alpha, iteration tag
+  bool ring_ready = false;
+  unsigned long long ring_clean_gen = ~0ull;   // ctx->state_gen the ring buffers were last zeroed for
 };
 
 void cg_fused_destroy(dpp_context* ctx) {
@@ -722,6 +796,9 @@ void cg_fused_destroy(dpp_context* ctx) {
     if (b) cudaFree(b);
   for (int32_t* b : F->bc_pad)
     if (b) cudaFree(b);
+  for (int j = 2; j < kXRing; ++j)
+    if (F->pring[j]) cudaFree(F->pring[j]);
+  if (F->d_xring) cudaFree(F->d_xring);
   if (F->d_count) cudaFree(F->d_count);
   delete F;
   ctx->fused = nullptr;
@@ -788,6 +865,31 @@ static int fused_state(dpp_context* ctx, FusedState** out) {
   return DPP_OK;
 }
 
+// deferred x update is used whenever the reduction epilogues run inside the kernels (single GPU or peer-memory
+// mailboxes): they are what records the step lengths.  DPP_NO_DEFER_X=1: x updated in the apply kernel.
+static bool defer_x_enabled(dpp_context* ctx) {
+  return (ctx->world == 1 || comm_ipc_ready(ctx)) && getenv("DPP_NO_DEFER_X") == nullptr;
+}
+
+// variant of the fused iteration the next launches will use (part of the CUDA-graph key of a CG batch)
+int cg_fused_variant(dpp_context* ctx) { return defer_x_enabled(ctx) ? 1 : 0; }
+
+static int ring_state(dpp_context* ctx, FusedState* F) {
+  if (F->ring_ready) return DPP_OK;
+  F->pring[0] = F->buf[1];
+  F->pring[1] = F->buf[2];
+  for (int j = 2; j < kXRing; ++j) {
+    DPP_CHECK(dev_alloc(ctx, &F->pring[j], 2 * F->field));
+    DPP_CUDA(cudaMemsetAsync(F->pring[j], 0, sizeof(double) * 2 * F->field, ctx->stream));
+  }
+  for (int nf = 1; nf <= 2; ++nf)
+    for (int j = 0; j < kXRing; ++j) DPP_CHECK(make_map(ctx, F, &F->tmr[nf - 1][j], F->pring[j], nf, true));
+  DPP_CHECK(dev_alloc(ctx, &F->d_xring, 2 * kXRing));
+  DPP_CUDA(cudaMemsetAsync(F->d_xring, 0, sizeof(double) * 2 * kXRing, ctx->stream));
+  F->ring_ready = true;
+  return DPP_OK;
+}
+
 // launch with programmatic stream serialization allowed (the kernel calls griddepcontrol.wait itself)
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -816,8 +918,9 @@ static FoldArgs fold_args(dpp_context* ctx, int slot, int post, int counter) {
   return f;
 }
 
-static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, const Coef& c, int pin_idx, double* pout,
-                        int slot, const double* dtab, bool want_dot, int* n_partial_blocks, bool interior_only = false) {
+static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, const Coef& c, const CUtensorMap& tm_pin,
+                        double* pout, int slot, const double* dtab, bool want_dot, int* n_partial_blocks,
+                        bool interior_only = false, bool defer_x = false) {
   const GridDesc& g = ctx->grid;
   const long long uplane = (long long)g.n[1] * g.n[2];
   if (ctx->owned_begin % uplane || ctx->owned_end % uplane) {
@@ -841,6 +944,8 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
   s.dtab = dtab;
   s.dom_lo = ctx->dom_lo; s.dom_hi = ctx->dom_hi;
   if (fused) s.fold = fold_args(ctx, slot, POST_CG_PAP, 0);
+  s.defer_x = defer_x ? 1 : 0;
+  if (defer_x) s.fold.xring = F->d_xring;
   s.j_lo = 0; s.j_hi = g.n[1]; s.k_lo = 0; s.k_hi = g.n[2];
   if (fused && interior_only && g.n[1] >= 3 && g.n[2] >= 3 && (g.n[0] >= 3 || g.n[0] == 1)) {
     // class-mask mode: every domain-boundary node is a constrained row whose p, w, x stay zero and whose
@@ -892,11 +997,11 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
   dim3 grid(nctas), block(TK, TY);
   const CUtensorMap* T = F->tm[nf - 1];
   if (nf == 2) {
-    if (fused) DPP_CUDA(launch_pdl(k_cg_fused_apply<2, true>, grid, block, sizeof(Smem<2>), ctx->stream, s, T[0], T[pin_idx], T[3]));
-    else k_cg_fused_apply<2, false><<<grid, block, sizeof(Smem<2>), ctx->stream>>>(s, T[0], T[pin_idx], T[3]);
+    if (fused) DPP_CUDA(launch_pdl(k_cg_fused_apply<2, true>, grid, block, sizeof(Smem<2>), ctx->stream, s, T[0], tm_pin, T[3]));
+    else k_cg_fused_apply<2, false><<<grid, block, sizeof(Smem<2>), ctx->stream>>>(s, T[0], tm_pin, T[3]);
   } else {
-    if (fused) DPP_CUDA(launch_pdl(k_cg_fused_apply<1, true>, grid, block, sizeof(Smem<1>), ctx->stream, s, T[0], T[pin_idx], T[3]));
-    else k_cg_fused_apply<1, false><<<grid, block, sizeof(Smem<1>), ctx->stream>>>(s, T[0], T[pin_idx], T[3]);
+    if (fused) DPP_CUDA(launch_pdl(k_cg_fused_apply<1, true>, grid, block, sizeof(Smem<1>), ctx->stream, s, T[0], tm_pin, T[3]));
+    else k_cg_fused_apply<1, false><<<grid, block, sizeof(Smem<1>), ctx->stream>>>(s, T[0], tm_pin, T[3]);
   }
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
@@ -953,6 +1058,13 @@ static int make_rargs(dpp_context* ctx, FusedState* F, int nf, int slot, const d
       a.zero_class[f] = F->bc_full[fld[f]];
     }
     a.fold = fold_args(ctx, slot, post, 1);
+    if (post == POST_CG_RZ && defer_x_enabled(ctx)) {
+      DPP_CHECK(ring_state(ctx, F));
+      a.defer_x = 1;
+      a.x = F->buf[4];
+      for (int j = 0; j < kXRing; ++j) a.pr[j] = F->pring[j];
+      a.xring = F->d_xring;
+    }
   }
   *out = a;
   return DPP_OK;
@@ -994,6 +1106,17 @@ int cg_fused_begin(dpp_context* ctx, int nf, const double* b) {
   for (int v : {1, 2, 4})
     for (int f = 0; f < nf; ++f)
       DPP_CUDA(cudaMemsetAsync(F->buf[v] + f * F->field, 0, sizeof(double) * F->field, ctx->stream));
+  if (defer_x_enabled(ctx)) {   // ring buffer 0 is p_old of the first iteration (beta = 0 times it: must be finite)
+    DPP_CHECK(ring_state(ctx, F));
+    DPP_CUDA(cudaMemsetAsync(F->d_xring, 0, sizeof(double) * 2 * kXRing, ctx->stream));
+    // rows a solve never writes (Dirichlet rows in class-mask mode, ghost planes) must read as zero: after a
+    // change of parameters / BCs / partition the buffers of earlier solves are wiped once
+    if (F->ring_clean_gen != ctx->state_gen) {
+      for (int j = 2; j < kXRing; ++j)
+        DPP_CUDA(cudaMemsetAsync(F->pring[j], 0, sizeof(double) * 2 * F->field, ctx->stream));
+      F->ring_clean_gen = ctx->state_gen;
+    }
+  }
   dim3 grid((unsigned)std::min<long long>((ctx->n_nodes + VT - 1) / VT, (long long)ctx->sm_count * 16), nf);
   k_pad_copy<<<grid, VT, 0, ctx->stream>>>(g, b, F->buf[0]);
   ctx->launches++;
@@ -1033,11 +1156,16 @@ int cg_fused_r_update(dpp_context* ctx, int nf, const int* fld, int slot, const 
 int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const int* fld, int slot, const double* dtab) {
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
-  const int pin = 1 + (int)(it & 1), pout = 1 + (int)((it + 1) & 1);
+  const bool defer = defer_x_enabled(ctx);
+  if (defer) DPP_CHECK(ring_state(ctx, F));
+  // classic: p ping-pongs between two buffers; deferred x: iteration `it` reads ring buffer it % 16 (p_{it-1}) and
+  // writes (it + 1) % 16 (p_it), so the last fifteen directions are still there when x is brought up to date
+  const CUtensorMap& tm_pin = defer ? F->tmr[nf - 1][it % kXRing] : F->tm[nf - 1][1 + (int)(it & 1)];
+  double* pout_buf = defer ? F->pring[(it + 1) % kXRing] : F->buf[1 + (int)((it + 1) & 1)];
   bool all_class_masked = true;
   for (int f = 0; f < nf; ++f) all_class_masked = all_class_masked && F->bc_full_gen[fld[f]] == ctx->bc_gen[fld[f]] && F->bc_full[fld[f]];
   int nb = 0;
-  DPP_CHECK(launch_apply(ctx, F, nf, true, c, pin, F->buf[pout], slot, dtab, true, &nb, all_class_masked));
+  DPP_CHECK(launch_apply(ctx, F, nf, true, c, tm_pin, pout_buf, slot, dtab, true, &nb, all_class_masked, defer));
   if (!(ctx->world == 1 || comm_ipc_ready(ctx))) DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
   if (all_class_masked) return DPP_OK;   // constrained rows never leave zero: no row fix-up needed
   // row elimination: w = p on constrained rows (identity rows of A_bc)
@@ -1070,7 +1198,7 @@ int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const 
   if (total > 0) {
     const long long uplane = (long long)ctx->grid.n[1] * ctx->grid.n[2];
     fx.w = F->buf[3];
-    fx.p = F->buf[pout];
+    fx.p = pout_buf;
     fx.field = F->field;
     fx.ob = (ctx->owned_begin / uplane) * F->plane;
     fx.oe = (ctx->owned_end / uplane) * F->plane;
@@ -1091,9 +1219,17 @@ int cg_fused_x_finalize(dpp_context* ctx, int nf, long long its, int slot, doubl
   const PadGeom g = pad_geom(ctx, F, nf);
   const long long nown = ctx->owned_end - ctx->owned_begin;
   dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((nown + VT - 1) / VT, (long long)ctx->sm_count * 16)), nf);
-  k_cg_x_finalize<<<grid, VT, 0, ctx->stream>>>(g, F->buf[4], F->buf[1 + (int)(its & 1)],
-                                                ctx->d_scalars + (size_t)slot * S_SLOT_SIZE, ctx->owned_begin,
-                                                ctx->owned_end, x);
+  if (defer_x_enabled(ctx)) {
+    DPP_CHECK(ring_state(ctx, F));
+    RingPtrs pr{};
+    for (int j = 0; j < kXRing; ++j) pr.p[j] = F->pring[j];
+    k_cg_x_finalize_ring<<<grid, VT, 0, ctx->stream>>>(g, F->buf[4], pr, ctx->d_scalars + (size_t)slot * S_SLOT_SIZE,
+                                                       F->d_xring, ctx->owned_begin, ctx->owned_end, x);
+  } else {
+    k_cg_x_finalize<<<grid, VT, 0, ctx->stream>>>(g, F->buf[4], F->buf[1 + (int)(its & 1)],
+                                                  ctx->d_scalars + (size_t)slot * S_SLOT_SIZE, ctx->owned_begin,
+                                                  ctx->owned_end, x);
+  }
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   return DPP_OK;
@@ -1137,7 +1273,7 @@ int cg_fused_halo_r(dpp_context* ctx, int nf, bool after_update, int slot) {
 int cg_fused_plain_apply(dpp_context* ctx, int nf, const Coef& c, bool want_dot, int* n_partial_blocks) {
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
-  return launch_apply(ctx, F, nf, false, c, 1, nullptr, 0, ctx->d_dtab, want_dot, n_partial_blocks);
+  return launch_apply(ctx, F, nf, false, c, F->tm[nf - 1][1], nullptr, 0, ctx->d_dtab, want_dot, n_partial_blocks);
 }
 
 double* cg_fused_buffer(dpp_context* ctx, int which) {

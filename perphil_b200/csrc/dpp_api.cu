@@ -449,7 +449,7 @@ void dpp_default_options(dpp_options* o) {
   o->max_it = 50000;       /* solvers/parameters.py:1 */
   o->gmres_restart = 30;   /* PETSc default */
   o->inner_max_it = 10000;
-  o->check_every = 8;
+  o->check_every = 16;   /* = the direction-ring length of the fused CG: batches replay as one CUDA graph */
   o->rtol = 1e-8;          /* solvers/parameters.py:14 */
   o->atol = 1e-12;         /* solvers/parameters.py:15 */
   o->dtol = 1e4;           /* PETSc default */

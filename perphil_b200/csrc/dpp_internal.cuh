@@ -242,6 +242,7 @@ struct FoldArgs {                  // reduction epilogue folded into the produci
   double* hist;
   int post;
   IpcReduce ipc;
+  double* xring;                   // deferred x update: step lengths + tags of the direction ring (else null)
 };
 struct IpcHalo {                   // kernel argument of the halo push (padded layout)
   double* peer_r[2];               // lower / upper neighbour's residual vector (null: none)

@@ -252,7 +252,8 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
     // the p ping-pong repeats with period 2: batches of an even number of iterations are identical launch
     // sequences -> replayed as one CUDA graph after the first (directly launched) batch
     unsigned long long key = mix(mix(mix(ctx->state_gen, (unsigned long long)op.nf * 16 + op.row * 4 + pc.type),
-                                     (unsigned long long)every), (unsigned long long)(uintptr_t)hist_device(ctx, slot));
+                                     (unsigned long long)every * 2 + cg_fused_variant(ctx)),
+                                 (unsigned long long)(uintptr_t)hist_device(ctx, slot));
     // Polling without a pipeline bubble: batch k+1 is enqueued BEFORE the host waits for the scalars of
     // batch k (copied into a pinned double buffer behind each batch).  Kernels launched past convergence
     // are no-ops on every rank alike (all ranks hold bit-identical scalars), so the speculative batch
@@ -263,7 +264,9 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
       for (auto& e : K->ev_poll) DPP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     auto enqueue = [&](int b) -> int {
-      if (kk == 0 || (every & 1)) DPP_CHECK(batch(kk));
+      // the launch sequence of a batch repeats when `every` is a multiple of the direction-ring length (16; the
+      // classic two-buffer ping-pong needs an even count)
+      if (kk == 0 || (every % 16) != 0) DPP_CHECK(batch(kk));
       else DPP_CHECK(run_graphed(ctx, K->cg_graph[slot], key, [&]() { return batch(kk); }));
       kk += every;
       DPP_CUDA(cudaMemcpyAsync(K->h_poll + (size_t)b * S_SLOT_SIZE, S, sizeof(double) * S_SLOT_SIZE, cudaMemcpyDeviceToHost,

@@ -50,6 +50,7 @@ int cg_xr_update(dpp_context* ctx, const VecLayout& L, double* x, double* r, con
 bool cg_fused_available(const dpp_context* ctx, int nf, int operator_mode, int pc_type);
 // (the reductions + PETSc bookkeeping after each kernel are folded into the kernels, or run as
 //  reduce_partials + NCCL when neither single-GPU nor peer-memory)
+int cg_fused_variant(dpp_context* ctx);   // 1: deferred x update (direction ring), 0: x updated in the apply kernel
 int cg_fused_table(dpp_context* ctx, const Coef& c, int nf, int pc_type, const int* fld, double* d_tab);
 int cg_fused_begin(dpp_context* ctx, int nf, const double* b);
 int cg_fused_rz_init(dpp_context* ctx, int nf, const int* fld, int slot, const double* dtab);

@@ -550,6 +550,36 @@ def test_fused_cg_equals_unfused_sequence(cells, preset, monkeypatch):
     assert rel_err(u1, ref.u) < 1e-7
 
 
+@pytest.mark.parametrize("cells", [(12, 12, 12), (33, 9, 40), (16, 16), (40, 40, 40)])
+@pytest.mark.parametrize("preset", ["jacobi", "none"])
+def test_deferred_x_update_is_bitwise_the_per_iteration_update(cells, preset, monkeypatch):
+    """The direction ring (x += alpha_k p_k applied for fifteen iterations at a time by the r-update kernel) performs
+    the same fused multiply-adds in the same order as the per-iteration update inside the apply kernel: identical
+    iteration counts, histories and solution BITS, whatever the iteration count modulo 15 (sizes chosen to stop at
+    different remainders), also for repeated solves on one handle and after a BC change."""
+    W, p, bcs, osys = make_problem(cells, 1)
+    params = {**(pb.B200_CG_JACOBI_PARAMS if preset == "jacobi" else pb.B200_CG_PARAMS), "b200_history": 4096}
+    monkeypatch.delenv("DPP_NO_DEFER_X", raising=False)
+    s1, u1, i1 = _solve_vec(W, p, bcs, params)
+    s1b, u1b, _ = _solve_vec(W, p, bcs, params)
+    monkeypatch.setenv("DPP_NO_DEFER_X", "1")
+    s2, u2, i2 = _solve_vec(W, p, bcs, params)
+    monkeypatch.delenv("DPP_NO_DEFER_X", raising=False)
+    assert s1.iteration_number == s2.iteration_number == s1b.iteration_number
+    assert np.array_equal(i1.history, i2.history)
+    assert np.array_equal(u1, u2) and np.array_equal(u1, u1b)
+    # partial Dirichlet set (no class mask: row fix-up kernel) on the same handle, then back
+    bcs2 = [bcs[0]]
+    s3, u3, _ = _solve_vec(W, p, bcs2, params)
+    monkeypatch.setenv("DPP_NO_DEFER_X", "1")
+    s4, u4, _ = _solve_vec(W, p, bcs2, params)
+    monkeypatch.delenv("DPP_NO_DEFER_X", raising=False)
+    assert s3.iteration_number == s4.iteration_number and np.array_equal(u3, u4)
+    s5, u5, _ = _solve_vec(W, p, bcs, params)
+    assert np.array_equal(u5, u1)
+    pb.release_handles()
+
+
 def test_fused_cg_partial_and_no_dirichlet():
     """Boundary nodes that are NOT constrained use the boundary-class reciprocal diagonal."""
     cells = (6, 5, 7)
