@@ -785,7 +785,8 @@ struct FusedState {
   double* pring[kXRing] = {};
   CUtensorMap tmr[2][kXRing];
   double* d_xring = nullptr;      // [2 * kXRing]: alpha, iteration tag
-  bool ring_ready = false;
+  bool ring_ready = false, ring_failed = false;
+  bool defer = false;             // the current solve defers the x update (decide_defer_x)
   unsigned long long ring_clean_gen = ~0ull;   // ctx->state_gen the ring buffers were last zeroed for
 };
 
@@ -866,20 +867,27 @@ static int fused_state(dpp_context* ctx, FusedState** out) {
 }
 
 // deferred x update is used whenever the reduction epilogues run inside the kernels (single GPU or peer-memory
-// mailboxes): they are what records the step lengths.  DPP_NO_DEFER_X=1: x updated in the apply kernel.
-static bool defer_x_enabled(dpp_context* ctx) {
-  return (ctx->world == 1 || comm_ipc_ready(ctx)) && getenv("DPP_NO_DEFER_X") == nullptr;
-}
-
-// variant of the fused iteration the next launches will use (part of the CUDA-graph key of a CG batch)
-int cg_fused_variant(dpp_context* ctx) { return defer_x_enabled(ctx) ? 1 : 0; }
-
+// mailboxes): they are what records the step lengths.  DPP_NO_DEFER_X=1: x updated in the apply kernel.  If the
+// direction ring cannot be allocated (16 vectors; 9.2 GB at 256^3) the handle silently keeps the two-buffer scheme:
+// same arithmetic, two more vector passes per iteration.
 static int ring_state(dpp_context* ctx, FusedState* F) {
   if (F->ring_ready) return DPP_OK;
+  if (F->ring_failed) return DPP_ERR_CUDA;
   F->pring[0] = F->buf[1];
   F->pring[1] = F->buf[2];
   for (int j = 2; j < kXRing; ++j) {
-    DPP_CHECK(dev_alloc(ctx, &F->pring[j], 2 * F->field));
+    if (dev_alloc(ctx, &F->pring[j], 2 * F->field) != DPP_OK) {
+      cudaGetLastError();
+      for (int i = 2; i < j; ++i) {
+        cudaFree(F->pring[i]);
+        ctx->device_bytes -= (int64_t)sizeof(double) * 2 * F->field;
+        F->pring[i] = nullptr;
+      }
+      F->pring[j] = nullptr;
+      F->ring_failed = true;
+      ctx->err.clear();
+      return DPP_ERR_CUDA;
+    }
     DPP_CUDA(cudaMemsetAsync(F->pring[j], 0, sizeof(double) * 2 * F->field, ctx->stream));
   }
   for (int nf = 1; nf <= 2; ++nf)
@@ -889,6 +897,15 @@ static int ring_state(dpp_context* ctx, FusedState* F) {
   F->ring_ready = true;
   return DPP_OK;
 }
+
+// decided at the start of every solve / timing run (cg_fused_table) and read by all launches of that solve
+static void decide_defer_x(dpp_context* ctx, FusedState* F) {
+  const bool want = (ctx->world == 1 || comm_ipc_ready(ctx)) && getenv("DPP_NO_DEFER_X") == nullptr;
+  F->defer = want && ring_state(ctx, F) == DPP_OK;
+}
+
+// variant of the fused iteration the launches of the current solve use (part of the CUDA-graph key of a CG batch)
+int cg_fused_variant(dpp_context* ctx) { return (ctx->fused != nullptr && ctx->fused->defer) ? 1 : 0; }
 
 // launch with programmatic stream serialization allowed (the kernel calls griddepcontrol.wait itself)
 template <typename... KArgs, typename... Args>
@@ -1058,8 +1075,7 @@ static int make_rargs(dpp_context* ctx, FusedState* F, int nf, int slot, const d
       a.zero_class[f] = F->bc_full[fld[f]];
     }
     a.fold = fold_args(ctx, slot, post, 1);
-    if (post == POST_CG_RZ && defer_x_enabled(ctx)) {
-      DPP_CHECK(ring_state(ctx, F));
+    if (post == POST_CG_RZ && F->defer) {
       a.defer_x = 1;
       a.x = F->buf[4];
       for (int j = 0; j < kXRing; ++j) a.pr[j] = F->pring[j];
@@ -1089,6 +1105,7 @@ static int r_blocks(const dpp_context* ctx, const RArgs& a) {
 int cg_fused_table(dpp_context* ctx, const Coef& c, int nf, int pc_type, const int* fld, double* d_tab) {
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
+  decide_defer_x(ctx, F);
   RArgs geom{};
   DPP_CHECK(make_rargs(ctx, F, nf, 0, d_tab, &geom, fld));
   k_dinv_table<<<1, 16, 0, ctx->stream>>>(ctx->grid, c, nf, pc_type == DPP_PC_JACOBI ? 1 : 0, geom.zero_class[0],
@@ -1106,8 +1123,7 @@ int cg_fused_begin(dpp_context* ctx, int nf, const double* b) {
   for (int v : {1, 2, 4})
     for (int f = 0; f < nf; ++f)
       DPP_CUDA(cudaMemsetAsync(F->buf[v] + f * F->field, 0, sizeof(double) * F->field, ctx->stream));
-  if (defer_x_enabled(ctx)) {   // ring buffer 0 is p_old of the first iteration (beta = 0 times it: must be finite)
-    DPP_CHECK(ring_state(ctx, F));
+  if (F->defer) {   // ring buffer 0 is p_old of the first iteration (beta = 0 times it: must be finite)
     DPP_CUDA(cudaMemsetAsync(F->d_xring, 0, sizeof(double) * 2 * kXRing, ctx->stream));
     // rows a solve never writes (Dirichlet rows in class-mask mode, ghost planes) must read as zero: after a
     // change of parameters / BCs / partition the buffers of earlier solves are wiped once
@@ -1156,8 +1172,7 @@ int cg_fused_r_update(dpp_context* ctx, int nf, const int* fld, int slot, const 
 int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const int* fld, int slot, const double* dtab) {
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
-  const bool defer = defer_x_enabled(ctx);
-  if (defer) DPP_CHECK(ring_state(ctx, F));
+  const bool defer = F->defer;
   // classic: p ping-pongs between two buffers; deferred x: iteration `it` reads ring buffer it % 16 (p_{it-1}) and
   // writes (it + 1) % 16 (p_it), so the last fifteen directions are still there when x is brought up to date
   const CUtensorMap& tm_pin = defer ? F->tmr[nf - 1][it % kXRing] : F->tm[nf - 1][1 + (int)(it & 1)];
@@ -1219,8 +1234,7 @@ int cg_fused_x_finalize(dpp_context* ctx, int nf, long long its, int slot, doubl
   const PadGeom g = pad_geom(ctx, F, nf);
   const long long nown = ctx->owned_end - ctx->owned_begin;
   dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((nown + VT - 1) / VT, (long long)ctx->sm_count * 16)), nf);
-  if (defer_x_enabled(ctx)) {
-    DPP_CHECK(ring_state(ctx, F));
+  if (F->defer) {
     RingPtrs pr{};
     for (int j = 0; j < kXRing; ++j) pr.p[j] = F->pring[j];
     k_cg_x_finalize_ring<<<grid, VT, 0, ctx->stream>>>(g, F->buf[4], pr, ctx->d_scalars + (size_t)slot * S_SLOT_SIZE,

@@ -161,6 +161,37 @@ def test_cell_block_kernel_equals_oracle_and_row_owner_kernel(N, distort, renumb
     h.close()
 
 
+def test_cell_block_kernel_with_separately_numbered_vertices():
+    """The coordinate field may be numbered independently of the pressure space (separate coord_cell_node_map): the
+    cell-block kernel then stages the vertex coordinates through its own per-block vertex lists."""
+    import sys
+    sys.path.insert(0, ".")
+    from tools.general_mesh import shuffled_distorted_hex
+    from perphil_b200.backend import DppHandle
+
+    N = 7
+    cnm, X, bn = shuffled_distorted_hex(N, 0.3, seed=3)
+    rng = np.random.default_rng(8)
+    vperm = rng.permutation(X.shape[0])                    # pressure node id -> vertex id
+    ccnm = vperm[cnm].astype(np.int32)
+    VX = np.empty_like(X); VX[vperm] = X
+    m2 = orc.Mesh(3, 1, (N, N, N), X, cnm, VX, ccnm, bn)
+    prm = orc.Params(k1=1.0, k2=1e-2, beta=1.0, mu=1.0)
+    g1, g2 = rng.standard_normal(bn.size), rng.standard_normal(bn.size)
+    osys = orc.build_system(m2, prm, (bn, g1, bn, g2))
+    for renumber in (False, True):
+        h = (DppHandle.from_mesh_arrays(3, 1, cnm, X, VX, ccnm, n_nodes=X.shape[0]) if renumber
+             else DppHandle(3, 1, cnm, VX, ccnm, n_nodes=X.shape[0]))
+        assert h.info().kernel_family == L.KERNEL_GENERAL
+        h.set_params(prm.k1, prm.k2, prm.beta, prm.mu)
+        h.set_dirichlet(0, bn, g1); h.set_dirichlet(1, bn, g2)
+        x = rng.standard_normal(osys.n_dof)
+        assert rel_err(h.apply(x), osys.A_bc @ x) < 5e-13
+        u, info = h.solve()
+        assert info.iterations == orc.solve_dpp_oracle(osys, "cg", "jacobi").iteration_number
+        h.close()
+
+
 @pytest.mark.parametrize("cells", [(6, 5, 7), (9, 12)])
 def test_apply_rectilinear_nonuniform_grid(cells):
     """Graded tensor grid: still lexicographic, so the structured family serves it through the
