@@ -34,6 +34,7 @@
 // mesh against 0.23 ms for its 1.52 GB of algorithmic traffic (58 B/node + 32 B/cell): DESIGN.md 4.3.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -44,7 +45,7 @@
 namespace dpp {
 
 constexpr int CB = 128;       // cells per block = threads per CTA
-constexpr int NLMAX = 384;    // node slots per block (8 x 4 x 4 cells have 225; Morton blocks of irregular meshes more)
+constexpr int NLMAX = 256;    // node slots per block (8 x 4 x 4 cells have 225; a block that needs more is halved)
 constexpr int ROUNDS = NLMAX / CB;
 
 struct CellBlocks {
@@ -200,17 +201,28 @@ struct StageArgs {
 template <int NF>
 __global__ void __launch_bounds__(VT) k_cells_stage(const StageArgs g) {
   if (g.skip_flag != nullptr && *g.skip_flag != 0.0) return;
-  for (long long s = (long long)blockIdx.x * VT + threadIdx.x; s < g.total_slots; s += (long long)gridDim.x * VT) {
-    const int node = g.blk_nodes[s];
+  constexpr int U = 4;   // slots per thread and trip: all index loads first, then the dependent gathers
+  const long long stride = (long long)gridDim.x * VT;
+  for (long long s0 = (long long)blockIdx.x * VT + threadIdx.x; s0 < g.total_slots; s0 += U * stride) {
+    int node[U];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      double v = 0.0;
-      if (node >= 0) {
-        v = g.x[f][node];
-        if (g.in_mask[f] != nullptr && g.in_mask[f][node]) v = 0.0;
+    for (int u = 0; u < U; ++u) node[u] = s0 + u * stride < g.total_slots ? g.blk_nodes[s0 + u * stride] : -1;
+    double v[NF][U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        v[f][u] = 0.0;
+        if (node[u] >= 0) {
+          v[f][u] = g.x[f][node[u]];
+          if (g.in_mask[f] != nullptr && g.in_mask[f][node[u]]) v[f][u] = 0.0;
+        }
       }
-      g.xblk[f * g.total_slots + s] = v;
-    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (s0 + u * stride < g.total_slots)
+#pragma unroll
+        for (int f = 0; f < NF; ++f) g.xblk[f * g.total_slots + s0 + u * stride] = v[f][u];
   }
 }
 
@@ -407,7 +419,7 @@ struct GatherArgs {
   const double* skip_flag;
 };
 
-template <int NF>
+template <int NF, int U>
 __global__ void __launch_bounds__(VT) k_cells_gather(const GatherArgs g) {
   __shared__ double sm[VT / 32];
   if (g.skip_flag != nullptr && *g.skip_flag != 0.0) return;
@@ -416,7 +428,23 @@ __global__ void __launch_bounds__(VT) k_cells_gather(const GatherArgs g) {
     double acc[NF];
 #pragma unroll
     for (int f = 0; f < NF; ++f) acc[f] = 0.0;
-    for (long long e = g.nd_ptr[node]; e < g.nd_ptr[node + 1]; ++e) {
+    const long long e0 = g.nd_ptr[node], e1 = g.nd_ptr[node + 1];
+    // a hexahedral node sits in at most 8 blocks: all slot loads first, then the dependent partials, added in
+    // ascending slot order; meshes with higher node valence take the tail loop
+    long long sl[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) sl[j] = e0 + j < e1 ? (long long)g.nd_slot[e0 + j] : -1;
+    double pv[NF][U];
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+#pragma unroll
+      for (int f = 0; f < NF; ++f) pv[f][j] = sl[j] >= 0 ? g.ypart[f * g.total_slots + sl[j]] : 0.0;
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+      if (sl[j] >= 0)
+#pragma unroll
+        for (int f = 0; f < NF; ++f) acc[f] += pv[f][j];
+    for (long long e = e0 + U; e < e1; ++e) {
       const long long s = g.nd_slot[e];
 #pragma unroll
       for (int f = 0; f < NF; ++f) acc[f] += g.ypart[f * g.total_slots + s];
@@ -705,8 +733,8 @@ int cells_apply(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks) {
   h.dot_partials = a.dot_partials;
   h.skip_flag = a.skip_flag;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((ctx->n_nodes + VT - 1) / VT, (long long)ctx->sm_count * 8));
-  if (a.nf == 2) k_cells_gather<2><<<blocks, VT, 0, ctx->stream>>>(h);
-  else k_cells_gather<1><<<blocks, VT, 0, ctx->stream>>>(h);
+  if (a.nf == 2) k_cells_gather<2, 8><<<blocks, VT, 0, ctx->stream>>>(h);
+  else k_cells_gather<1, 8><<<blocks, VT, 0, ctx->stream>>>(h);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   if (n_partial_blocks) *n_partial_blocks = blocks;
