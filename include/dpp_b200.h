@@ -95,7 +95,8 @@ typedef struct {
   int64_t n_nodes, n_cells, n_owned_nodes;
   int32_t rank, world;
   int32_t sm_count;
-  int32_t peer_memory;       /* 1: CUDA IPC halo push + mailbox allreduce active (dpp_comm_ipc_import) */
+  int32_t peer_memory;       /* bit 0: mailbox all-reduce, bit 1: fused-CG halo push, bit 2: halo inboxes for generic
+                                vectors (all over CUDA IPC peer memory, dpp_comm_ipc_import); 0: NCCL only */
   int64_t device_bytes;      /* device memory held by the handle */
 } dpp_info;
 

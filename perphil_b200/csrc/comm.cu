@@ -74,9 +74,11 @@ struct Neighbor {
 struct IpcBlob {  // what every rank publishes (POD; all-gathered by the host layer)
   cudaIpcMemHandle_t r_handle;
   cudaIpcMemHandle_t mbox_handle;
+  cudaIpcMemHandle_t box_handle;   // halo inbox (generic vectors; see comm_halo_exchange)
   int64_t field, plane;      // padded strides of the residual vector (doubles)
+  int64_t box_cap;           // doubles per (parity, side) section of the inbox
   int32_t i_begin, i_end;    // owned local planes
-  int32_t rank, valid;       // valid: bit 0 mailbox handle, bit 1 residual-vector handle
+  int32_t rank, valid;       // valid: bit 0 mailbox handle, bit 1 residual-vector handle, bit 2 halo inbox
 };
 
 struct Comm {
@@ -89,6 +91,13 @@ struct Comm {
   double* mbox_peer[kMaxIpcRanks] = {};   // mapped mailboxes of the other ranks
   double* r_peer[2] = {nullptr, nullptr}; // mapped residual vectors of rank-1 / rank+1
   long long r_peer_field[2] = {0, 0}, r_peer_ghost_off[2] = {0, 0};
+  // halo inbox: neighbours store their boundary planes of ANY vector here (peer writes over NVLink), then a flag
+  bool ipc_box = false;
+  double* box = nullptr;                  // own inbox: [2 parities][2 sides][box_cap] + flags
+  long long box_cap = 0;
+  double* box_peer[2] = {nullptr, nullptr};   // mapped inbox of rank-1 / rank+1
+  long long box_peer_cap[2] = {0, 0};
+  unsigned long long* d_hseq = nullptr;   // device: number of halo exchanges executed, arrival counter, error flag
   std::vector<void*> mapped;              // everything opened with cudaIpcOpenMemHandle
 };
 
@@ -121,6 +130,101 @@ __global__ void k_unpack(long long n, const int32_t* __restrict__ idx, double* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Peer-memory halo exchange for ANY field-blocked vector (the unfused Krylov paths, Q2, GMRES, Picard).  Every
+// rank owns an inbox [2 parities][2 sides][cap]; exchange number s (device counter, the same on all ranks because
+// all ranks execute the same sequence of exchanges) works on parity s & 1:
+//   k_halo_put   stores this rank's boundary planes into the neighbours' inboxes (NVLink peer writes); every block
+//                reports in through a gpu-scope fence + arrival counter, the last block executes ONE
+//                fence.acq_rel.sys (cumulative over all blocks' stores) and then writes s into the neighbours'
+//                flag words;
+//   k_halo_get   polls its own flag words (ld.acquire.sys) until both neighbours' planes of exchange s have landed,
+//                then copies them from the inbox into the ghost planes of the vector.
+// Two parities suffice: a neighbour can start exchange s + 1 before this rank has emptied section s (other parity),
+// but exchange s + 2 needs this rank's data of s + 1, which this rank sends after it emptied s (stream order).
+// Replaces a grouped ncclSend/ncclRecv (~35 us per exchange on two B200s) by two small kernels.
+// ------------------------------------------------------------------------------------------------------------
+struct HaloSide {
+  double* peer_data;                 // neighbour's inbox section base for my side (parity 0), null: no neighbour
+  unsigned long long* peer_flag;     // neighbour's flag word for my side
+  const double* own_data;            // my inbox section base for that neighbour's side (parity 0)
+  const unsigned long long* own_flag;
+  long long peer_par_stride, own_par_stride;   // doubles between the two parities
+  long long n_send, n_recv, send0, recv0;
+  const int32_t* send_idx;           // null: contiguous from send0
+  const int32_t* recv_idx;
+};
+struct HaloArgs {
+  HaloSide side[2];
+  double* f[2];
+  int nf;
+  unsigned long long* hseq;          // [0] exchanges done, [1] arrival counter, [2] error flag
+};
+
+__global__ void __launch_bounds__(256) k_halo_put(const HaloArgs a) {
+  const unsigned long long seq = a.hseq[0] + 1;
+  const int par = (int)(seq & 1ull);
+  for (int s = 0; s < 2; ++s) {
+    const HaloSide& h = a.side[s];
+    if (h.peer_data == nullptr) continue;
+    double* dst = h.peer_data + par * h.peer_par_stride;
+    for (int f = 0; f < a.nf; ++f)
+      for (long long i = blockIdx.x * 256ll + threadIdx.x; i < h.n_send; i += gridDim.x * 256ll)
+        dst[f * h.n_send + i] = a.f[f][h.send_idx != nullptr ? (long long)h.send_idx[i] : h.send0 + i];
+  }
+  __shared__ int last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(a.hseq + 1), 1u);
+    last = t == gridDim.x - 1;
+    if (last) {
+      *reinterpret_cast<unsigned*>(a.hseq + 1) = 0u;
+      __threadfence();
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      for (int s = 0; s < 2; ++s)
+        if (a.side[s].peer_flag != nullptr) *reinterpret_cast<volatile unsigned long long*>(a.side[s].peer_flag) = seq;
+      a.hseq[0] = seq;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_halo_get(const HaloArgs a) {
+  const unsigned long long seq = a.hseq[0];   // written by k_halo_put of this exchange (stream order)
+  const int par = (int)(seq & 1ull);
+  __shared__ int bad;
+  if (threadIdx.x == 0) {
+    bad = 0;
+    const long long t0 = clock64();
+    for (int s = 0; s < 2; ++s) {
+      if (a.side[s].own_flag == nullptr) continue;
+      unsigned long long v;
+      while (true) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.side[s].own_flag) : "memory");
+        if (v >= seq) break;
+        if (clock64() - t0 > 60000000000LL) {   // ~30 s: a peer died; report instead of hanging the GPU
+          bad = 1;
+          a.hseq[2] = 1ull;
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (bad) return;
+  for (int s = 0; s < 2; ++s) {
+    const HaloSide& h = a.side[s];
+    if (h.own_data == nullptr) continue;
+    const double* src = h.own_data + par * h.own_par_stride;
+    for (int f = 0; f < a.nf; ++f)
+      for (long long i = blockIdx.x * 256ll + threadIdx.x; i < h.n_recv; i += gridDim.x * 256ll) {
+        double v;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(src + f * h.n_recv + i) : "memory");
+        a.f[f][h.recv_idx != nullptr ? (long long)h.recv_idx[i] : h.recv0 + i] = v;
+      }
+  }
+}
+
 bool contiguous(const int32_t* v, int64_t n) {
   for (int64_t i = 1; i < n; ++i)
     if (v[i] != v[0] + i) return false;
@@ -132,6 +236,41 @@ bool contiguous(const int32_t* v, int64_t n) {
 int comm_halo_exchange(dpp_context* ctx, double* const* fields, int nf) {
   Comm* C = ctx->comm;
   if (!C || ctx->world <= 1) return DPP_OK;
+  if (C->ipc && C->ipc_box) {
+    HaloArgs a{};
+    a.nf = nf;
+    a.f[0] = fields[0];
+    a.f[1] = nf == 2 ? fields[1] : nullptr;
+    a.hseq = C->d_hseq;
+    long long work = 1;
+    for (Neighbor& nb : C->nbrs) {
+      const int s = nb.peer < ctx->rank ? 0 : 1;        // the neighbour below / above me
+      HaloSide& h = a.side[s];
+      // in the neighbour's inbox I am its upper (s == 0) / lower (s == 1) side
+      const int my_side_there = s == 0 ? 1 : 0;
+      const long long pcap = C->box_peer_cap[s];
+      if ((long long)nf * nb.n_send > pcap || (long long)nf * nb.n_recv > C->box_cap) {
+        ctx->set_error("halo inbox too small for this exchange");
+        return DPP_ERR_INVALID;
+      }
+      h.peer_data = C->box_peer[s] + my_side_there * pcap;
+      h.peer_par_stride = 2 * pcap;
+      h.peer_flag = reinterpret_cast<unsigned long long*>(C->box_peer[s] + 4 * pcap) + my_side_there;
+      h.own_data = C->box + s * C->box_cap;
+      h.own_par_stride = 2 * C->box_cap;
+      h.own_flag = reinterpret_cast<unsigned long long*>(C->box + 4 * C->box_cap) + s;
+      h.n_send = nb.n_send; h.n_recv = nb.n_recv; h.send0 = nb.send0; h.recv0 = nb.recv0;
+      h.send_idx = nb.send_contig ? nullptr : nb.d_send_idx;
+      h.recv_idx = nb.recv_contig ? nullptr : nb.d_recv_idx;
+      work = std::max<long long>(work, std::max(nb.n_send, nb.n_recv));
+    }
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((work + 255) / 256, 2LL * ctx->sm_count));
+    k_halo_put<<<blocks, 256, 0, ctx->stream>>>(a);
+    k_halo_get<<<blocks, 256, 0, ctx->stream>>>(a);
+    ctx->launches += 2;
+    DPP_CUDA(cudaGetLastError());
+    return DPP_OK;
+  }
   for (Neighbor& nb : C->nbrs) {
     if (nb.n_send > 0 && !nb.send_contig) {
       const int blocks = (int)std::min<int64_t>((nb.n_send + 255) / 256, 1024);
@@ -194,6 +333,16 @@ int comm_allreduce_sum(dpp_context* ctx, double* d_vals, int n) {
 
 bool comm_ipc_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc; }
 bool comm_ipc_halo_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc && ctx->comm->ipc_halo; }
+bool comm_ipc_box_ready(const dpp_context* ctx) { return ctx->comm != nullptr && ctx->comm->ipc && ctx->comm->ipc_box; }
+// 1 when a peer never delivered a halo plane (k_halo_get timed out); synchronises the stream
+int comm_halo_failed(dpp_context* ctx) {
+  Comm* C = ctx->comm;
+  if (!C || !C->d_hseq || !C->ipc_box) return 0;
+  unsigned long long v = 0;
+  if (cudaMemcpyAsync(&v, C->d_hseq + 2, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
+  cudaStreamSynchronize(ctx->stream);
+  return v != 0 ? 1 : 0;
+}
 
 // Measurement switches that deliberately break the protocol (profiles/r01_exchange_cost.md) exist only in
 // builds made with -DDPP_MEASUREMENT (make MEASUREMENT=1); the release library ignores the variables, so
@@ -257,6 +406,8 @@ void comm_destroy(dpp_context* ctx) {
   if (!C) return;
   for (void* m : C->mapped) cudaIpcCloseMemHandle(m);
   if (C->mbox) cudaFree(C->mbox);
+  if (C->box) cudaFree(C->box);
+  if (C->d_hseq) cudaFree(C->d_hseq);
   for (Neighbor& nb : C->nbrs) {
     void* p[] = {nb.d_send_idx, nb.d_recv_idx, nb.d_sendbuf, nb.d_recvbuf};
     for (void* q : p)
@@ -328,6 +479,27 @@ int dpp_comm_ipc_export(dpp_handle ctx, void* blob_out) {
     }
     if (cudaIpcGetMemHandle(&b.mbox_handle, C->mbox) == cudaSuccess) b.valid |= 1;
     else cudaGetLastError();
+    if ((b.valid & 1) && !C->nbrs.empty() && !getenv("DPP_NO_IPC_BOX")) {   // halo inbox for generic vectors
+      long long cap = 0;
+      for (const dpp::Neighbor& nb : C->nbrs) cap = std::max<long long>(cap, 2 * std::max(nb.n_send, nb.n_recv));
+      cap = (cap + 1) & ~1ll;
+      if (!C->box || C->box_cap != cap) {
+        if (C->box) cudaFree(C->box);
+        C->box = nullptr;
+        C->box_cap = cap;
+        DPP_CHECK(dpp::dev_alloc(ctx, &C->box, 4 * cap + 2));
+        DPP_CUDA(cudaMemset(C->box, 0, sizeof(double) * (4 * cap + 2)));
+        if (!C->d_hseq) DPP_CHECK(dpp::dev_alloc(ctx, &C->d_hseq, 4));
+        DPP_CUDA(cudaMemset(C->d_hseq, 0, sizeof(unsigned long long) * 4));
+        DPP_CUDA(cudaDeviceSynchronize());
+      }
+      if (cudaIpcGetMemHandle(&b.box_handle, C->box) == cudaSuccess) {
+        b.box_cap = cap;
+        b.valid |= 4;
+      } else {
+        cudaGetLastError();
+      }
+    }
     long long field = 0, plane = 0;
     double* r = dpp::cg_fused_r_buffer(ctx, &field, &plane);   // only the fused (uniform Q1) path has one
     if (r != nullptr && (b.valid & 1)) {
@@ -371,6 +543,28 @@ int dpp_comm_ipc_import(dpp_handle ctx, const void* blobs) {
     C->mbox_peer[r] = static_cast<double*>(m);
   }
   C->ipc = true;
+  // halo inboxes of the two neighbours (all ranks must have one: the protocol is the same everywhere)
+  bool all_box = true;
+  for (int r = 0; r < ctx->world; ++r) all_box = all_box && (B[r].valid & 4);
+  C->ipc_box = false;
+  if (all_box) {
+    bool ok = true;
+    for (int s = 0; s < 2 && ok; ++s) {
+      const int peer = s == 0 ? ctx->rank - 1 : ctx->rank + 1;
+      C->box_peer[s] = nullptr;
+      if (peer < 0 || peer >= ctx->world) continue;
+      void* m = nullptr;
+      if (cudaIpcOpenMemHandle(&m, B[peer].box_handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+        break;
+      }
+      C->mapped.push_back(m);
+      C->box_peer[s] = static_cast<double*>(m);
+      C->box_peer_cap[s] = B[peer].box_cap;
+    }
+    C->ipc_box = ok;
+  }
   for (int s = 0; s < 2 && all_r; ++s) {
     const int peer = s == 0 ? ctx->rank - 1 : ctx->rank + 1;
     if (peer < 0 || peer >= ctx->world) continue;
@@ -393,7 +587,7 @@ int dpp_comm_ipc_import(dpp_handle ctx, const void* blobs) {
 
 int dpp_comm_ipc_disable(dpp_handle ctx) {
   if (!ctx) return DPP_ERR_INVALID;
-  if (ctx->comm) ctx->comm->ipc = ctx->comm->ipc_halo = false;
+  if (ctx->comm) ctx->comm->ipc = ctx->comm->ipc_halo = ctx->comm->ipc_box = false;
   return DPP_OK;
 }
 

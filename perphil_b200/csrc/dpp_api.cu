@@ -217,7 +217,8 @@ int dpp_get_info(dpp_handle ctx, dpp_info* info) {
   info->rank = ctx->rank;
   info->world = ctx->world;
   info->sm_count = ctx->sm_count;
-  info->peer_memory = (dpp::comm_ipc_ready(ctx) ? 1 : 0) | (dpp::comm_ipc_halo_ready(ctx) ? 2 : 0);
+  info->peer_memory = (dpp::comm_ipc_ready(ctx) ? 1 : 0) | (dpp::comm_ipc_halo_ready(ctx) ? 2 : 0) |
+                      (dpp::comm_ipc_box_ready(ctx) ? 4 : 0);
   info->device_bytes = ctx->device_bytes;
   return DPP_OK;
 }

@@ -252,6 +252,8 @@ struct IpcHalo {                   // kernel argument of the halo push (padded l
 };
 bool comm_ipc_ready(const dpp_context* ctx);        // mailbox all-reduce
 bool comm_ipc_halo_ready(const dpp_context* ctx);   // + halo push into the neighbours' residual vectors
+bool comm_ipc_box_ready(const dpp_context* ctx);    // + halo inboxes for generic vectors (comm_halo_exchange)
+int comm_halo_failed(dpp_context* ctx);             // a k_halo_get timed out
 IpcReduce comm_ipc_reduce_args(dpp_context* ctx);   // world == 1 when the mailbox path is not active
 IpcHalo comm_ipc_halo(const dpp_context* ctx);
 // residual buffer registration (cg_fused_uniform.cu owns the memory)

@@ -1074,6 +1074,10 @@ int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_r
       rc = DPP_ERR_INVALID;
   }
   DPP_CHECK(rc);
+  if (ctx->world > 1 && comm_halo_failed(ctx)) {
+    ctx->set_error("a neighbour rank never delivered its halo planes (peer-memory halo inbox timed out)");
+    return DPP_ERR_NCCL;
+  }
   if (out.reason == DPP_DIVERGED_COMM_TIMEOUT) {
     ctx->set_error("a peer rank never arrived at a Krylov reduction (peer-memory mailbox timed out)");
     return DPP_ERR_NCCL;
