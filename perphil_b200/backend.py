@@ -96,6 +96,7 @@ class DppHandle:
             raise ValueError("numbering map must have one entry per node")
         self._check(self._lib.dpp_set_numbering(self._h, _ptr(perm)), "dpp_set_numbering")
         self._perm = perm
+        self._uploaded = {k: v for k, v in self._uploaded.items() if k == "params"}   # the library dropped its BCs
 
     # -- plumbing
     def _check(self, rc: int, what: str):

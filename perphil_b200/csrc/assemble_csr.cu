@@ -246,7 +246,54 @@ __global__ void __launch_bounds__(NUM_THREADS) k_numeric(const NumArgs g) {
   int b0 = 0, b1 = 0, b2 = 0;   // lane as trial node b / as Gauss point q
   if (DIM == 2) { b1 = lane / P1; b2 = lane % P1; }
   else { b0 = lane / (P1 * P1); b1 = (lane / P1) % P1; b2 = lane % P1; }
-  for (long long e = e0; e < e1; ++e) {
+  // Fast path (every incident cell affine, <= 2^DIM of them: the common case): all loads of the row's cells are
+  // issued before any is used -- two memory round trips per row instead of two per incident cell (the sequential
+  // loop below ran at 0.22 of the nnz * 12 B model, bound by that latency chain).  The shared-memory accumulation
+  // keeps the ascending cell order: same bits as the loop.
+  constexpr int NCMAX = 1 << DIM;
+  long long e_start = e0;
+  if (e1 - e0 <= NCMAX) {
+    long long cell[NCMAX];
+    int aa[NCMAX];
+#pragma unroll
+    for (int c = 0; c < NCMAX; ++c) {
+      cell[c] = e0 + c < e1 ? (long long)g.adj_cell[e0 + c] : -1;
+      aa[c] = e0 + c < e1 ? (int)g.adj_loc[e0 + c] : 0;
+    }
+    double kabv[NCMAX], mabv[NCMAX];
+    int pp[NCMAX];
+    bool all_affine = true;
+#pragma unroll
+    for (int c = 0; c < NCMAX; ++c) {
+      kabv[c] = mabv[c] = 0.0;
+      pp[c] = 0;
+      if (cell[c] >= 0) {
+        const double* gm = g.geom + cell[c] * 8;
+        all_affine = all_affine && gm[7] != 0.0;
+        if (lane < NPC) {
+          const int ab = aa[c] * NPC + lane;
+          double kab = 0.0;
+#pragma unroll
+          for (int s = 0; s < 6; ++s) kab = fma(gm[s], TAB_SMEM ? sT[s * NPC * NPC + ab] : __ldg(g.tabs + s * 729 + ab), kab);
+          kabv[c] = kab;
+          mabv[c] = gm[6] * (TAB_SMEM ? sT[6 * NPC * NPC + ab] : __ldg(g.tabs + 6 * 729 + ab));
+          pp[c] = (int)g.pos[(cell[c] * NPC + aa[c]) * NPC + lane];
+        }
+      }
+    }
+    if (all_affine) {   // uniform over the group: every lane tests the same cells
+#pragma unroll
+      for (int c = 0; c < NCMAX; ++c) {
+        if (cell[c] >= 0 && lane < NPC) {
+          sK[grp][pp[c]] += kabv[c];
+          sM[grp][pp[c]] += mabv[c];
+        }
+        __syncwarp(gmask);
+      }
+      e_start = e1;   // done
+    }
+  }
+  for (long long e = e_start; e < e1; ++e) {
     const long long cell = g.adj_cell[e];
     const int a = g.adj_loc[e];
     const double* gm = g.geom + cell * 8;
@@ -312,9 +359,22 @@ __global__ void __launch_bounds__(NUM_THREADS) k_numeric(const NumArgs g) {
   const long long n = g.n;
   const bool m0 = g.mask[r] != 0, m1 = g.mask[n + r] != 0;
   const long long p0 = 2 * gb, p1 = 2 * g.nnz_g + 2 * gb;
-  for (int t = lane; t < len; t += LANES) {
-    const long long c = g.g_cols[gb + t];
-    const bool c0 = g.mask[c] != 0, c1 = g.mask[n + c] != 0;
+  constexpr int NW = (MAXROW + LANES - 1) / LANES;   // entries per lane: column loads first, then the dependent masks
+  long long cc[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) cc[w] = lane + w * LANES < len ? (long long)g.g_cols[gb + lane + w * LANES] : -1;
+  bool c0v[NW], c1v[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    c0v[w] = cc[w] >= 0 && g.mask[cc[w]] != 0;
+    c1v[w] = cc[w] >= 0 && g.mask[n + cc[w]] != 0;
+  }
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    const int t = lane + w * LANES;
+    if (t >= len) continue;
+    const long long c = cc[w];
+    const bool c0 = c0v[w], c1 = c1v[w];
     const double K = sK[grp][t], M = sM[grp][t];
     const bool diag = (c == r);
     double v00 = g.c.cK[0][0] * K + g.c.cM[0][0] * M, v01 = g.c.cK[0][1] * K + g.c.cM[0][1] * M;

@@ -299,3 +299,38 @@ def test_slice_along_x_is_point_evaluation_of_the_fe_function():
             assert np.abs(v - (2.0 * x ** deg + 3.0 * y * x)).max() < 1e-13
     with pytest.raises(ValueError):
         pb.slice_along_x(f, 1.5)
+
+
+def test_morton_permutation_is_a_locality_preserving_permutation():
+    """lattice.morton_permutation (numbering map of non-lattice meshes for the element-based kernels)."""
+    from perphil_b200.lattice import detect_lattice, morton_permutation
+    import sys
+    sys.path.insert(0, ".")
+    from tools.general_mesh import shuffled_distorted_hex
+
+    cnm, X, bn = shuffled_distorted_hex(8, 0.25, seed=2)
+    assert cnm.shape == (512, 8) and X.shape == (729, 3) and bn.size == 729 - 343
+    assert detect_lattice(3, 1, cnm, X, X, cnm) is None          # distorted: not a tensor grid
+    perm = morton_permutation(X)
+    assert perm.dtype == np.int32 and np.array_equal(np.sort(perm), np.arange(729))
+    # locality: the 8 nodes of a cell end up close in the new numbering (random numbering: spread ~ n / 2)
+    spread = np.ptp(perm[cnm], axis=1)
+    assert np.median(spread) < 729 / 6 and np.median(np.ptp(cnm, axis=1)) > 729 / 3
+    # an undistorted shuffled lattice IS detected and gets the lexicographic map instead
+    cnm2, X2, _ = shuffled_distorted_hex(5, 0.0, seed=3)
+    lat = detect_lattice(3, 1, cnm2, X2, X2, cnm2)
+    assert lat is not None and lat.cells == (5, 5, 5)
+
+
+def test_bench_cpu_arm_sets_its_thread_count_itself(monkeypatch):
+    """under torch.distributed.run OMP_NUM_THREADS=1 silently changed the CPU baseline."""
+    import bench
+    from oracle import c_oracle as co
+
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    n = bench.host_threads()
+    assert n >= 1 and isinstance(bench.cpu_model(), str)
+    out = bench.cpu_baseline(12, single_thread_size=8)
+    assert out["cores"] == n == co.num_threads() and out["kind"] == "port"
+    assert out["single_thread"]["cores"] == 1 and out["single_thread"]["value"] > 0
+    assert out["iterations"] == co.manufactured_system((12, 12, 12), 1).cg("jacobi").iteration_number
