@@ -395,6 +395,15 @@ int structured_detect_and_setup(dpp_context* ctx, const int32_t* cnm, const doub
     ctx->uni_k_off[a] = -1.0 / h0;
   }
   ctx->grid_uniform = uni;
+  bool uni2 = (p == 2);
+  for (int a = 0; a < 3 && uni2; ++a) {
+    const std::vector<double>& v = ax[a];
+    if (v.size() < 2) continue;   // dummy axis
+    ctx->uni_h[a] = v[1] - v[0];
+    for (size_t t = 2; t < v.size(); ++t)
+      if (std::fabs((v[t] - v[t - 1]) - ctx->uni_h[a]) > 1e-12 * std::fabs(ctx->uni_h[a])) uni2 = false;
+  }
+  ctx->q2_uniform = uni2;
   if (const char* e = getenv("DPP_FORCE_TABLE_KERNEL")) ctx->force_table_kernel = (e[0] == '1');
   return DPP_OK;
 }

@@ -18,7 +18,8 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// block-wide sum in a fixed order; result valid in thread 0 (linear thread id; VT threads per block)
+// block-wide sum in a fixed order; result valid in thread 0 (linear thread id; NTH threads per block)
+template <int NTH = VT>
 __device__ __forceinline__ double block_sum(double v, double* sm /*[VT/32]*/) {
   v = warp_sum(v);
   const int tid = threadIdx.x + threadIdx.y * blockDim.x;
@@ -29,7 +30,7 @@ __device__ __forceinline__ double block_sum(double v, double* sm /*[VT/32]*/) {
   double t = 0.0;
   if (tid == 0) {
 #pragma unroll
-    for (int w = 0; w < VT / 32; ++w) t += sm[w];
+    for (int w = 0; w < NTH / 32; ++w) t += sm[w];
   }
   return t;
 }
@@ -125,6 +126,7 @@ struct FoldPre {                  // shared-memory snapshot taken after griddepc
 //     completed before the block reported in) skip it.
 //   ipc.ll = 0 (DPP_MBOX_LL=0): values, system fence, separate flag word (two traversals).
 // sm: kFinishSmem doubles of shared memory.
+template <int NTH = VT>   // threads of the calling block (<= VT: the shared-memory layout is sized for VT)
 __device__ __forceinline__ void finish_reduction(const double* __restrict__ partials, int nblocks, int width, double* S,
                                                  double* hist, int post, int out_offset, const IpcReduce& ipc,
                                                  double* sm, bool sys_release = true, FoldPre pre = FoldPre{nullptr, nullptr},
@@ -136,7 +138,7 @@ __device__ __forceinline__ void finish_reduction(const double* __restrict__ part
   if (tid == 0) *timed_out = 0;
   if (width == 2) {   // both sums in one pass (the r-update epilogue sits on the critical path of every iteration)
     double v0 = 0.0, v1 = 0.0;
-    for (int b = tid; b < nblocks; b += VT) {
+    for (int b = tid; b < nblocks; b += NTH) {
       const double2 pv = *reinterpret_cast<const double2*>(partials + (size_t)b * 2);
       v0 += pv.x;
       v1 += pv.y;
@@ -153,7 +155,7 @@ __device__ __forceinline__ void finish_reduction(const double* __restrict__ part
     if (tid == 0) {
       double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-      for (int w = 0; w < VT / 32; ++w) {
+      for (int w = 0; w < NTH / 32; ++w) {
         t0 += sm[w];
         t1 += recv[w];
       }
@@ -163,8 +165,8 @@ __device__ __forceinline__ void finish_reduction(const double* __restrict__ part
   } else {
     for (int w = 0; w < width; ++w) {
       double v = 0.0;
-      for (int b = tid; b < nblocks; b += VT) v += partials[(size_t)b * width + w];
-      const double t = block_sum(v, sm);
+      for (int b = tid; b < nblocks; b += NTH) v += partials[(size_t)b * width + w];
+      const double t = block_sum<NTH>(v, sm);
       if (tid == 0) vals[w] = t;
     }
   }

@@ -40,6 +40,7 @@ namespace dpp {
 
 namespace {
 
+constexpr int kClsPerField = 64;   // reciprocal-diagonal classes per field: (px py pz) * 8 + (bx by bz)
 constexpr int TK = 32;
 constexpr int TY = 8;
 constexpr int TJ = 2 * TY;
@@ -69,7 +70,7 @@ struct FArgs {
   int ntj, ntk, nseg;
   int j_lo, j_hi, k_lo, k_hi;  // nodes of a plane that are computed (class-mask mode: interior only)
   const double* S;           // scalar slot of the solver (null in plain-apply mode)
-  const double* dtab;        // [2][8] reciprocal diagonal per boundary class bx*4 + by*2 + bz
+  const double* dtab;        // [2][64] reciprocal diagonal per class: (node parity px py pz) * 8 + (boundary bx by bz); Q1: parity 0
   int dom_lo, dom_hi;        // local plane 0 / n[0]-1 lies on the domain boundary (else it is a ghost plane)
   int defer_x;               // x is updated by the r-update kernel from the direction ring, not here
   FoldArgs fold;             // <p,Ap> reduction epilogue run by the last CTA
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
   }
   // the class table is written once per solve, before the first kernel of the iteration: safe to fetch while
   // the previous kernel of the stream is still in its reduction epilogue
-  if (tid < 16) sm.dtab[tid] = (FUSED && tid < 8 * NF) ? s.dtab[tid] : 1.0;
+  if (tid < 16) sm.dtab[tid] = (FUSED && tid < 8 * NF) ? s.dtab[(tid >> 3) * kClsPerField + (tid & 7)] : 1.0;
   pdl_wait();  // everything below reads what the previous kernel of the stream produced
   if (FUSED && s.S[S_REASON] != 0.0) return;
   if (FUSED && s.fold.enabled) {
@@ -424,6 +425,7 @@ struct RArgs {
   int zero_class[2];         // field f: every domain-boundary node is a Dirichlet node (and no other)
   FoldArgs fold;
   IpcHalo halo;              // peer residual vectors: boundary planes are stored there as well
+  int q2;                    // degree-2 lattice: odd indices are mid nodes (their own diagonal class)
   int defer_x;               // deferred x update: every (kXRing - 1)-th iteration x += sum alpha_k p_k from the ring
   double* x;
   const double* pr[kXRing];  // direction ring (padded, field-blocked)
@@ -455,7 +457,8 @@ __device__ __forceinline__ int node_class(const RArgs& a, unsigned q) {
   const int bx = (a.ni > 1 && ((i == 0 && a.dom_lo) || (i == a.ni - 1 && a.dom_hi))) ? 4 : 0;  // dummy axis: no class
   const int by = (j == 0 || j == a.nj - 1) ? 2 : 0;
   const int bz = (k == 0 || k == a.nk - 1) ? 1 : 0;
-  return bx + by + bz;
+  const int par = a.q2 ? (int)(((i & 1u) << 2) | ((j & 1u) << 1) | (k & 1u)) : 0;
+  return par * 8 + bx + by + bz;
 }
 
 // Streaming kernel: every thread walks its block's range in aligned PAIRS of nodes (16-byte loads and stores;
@@ -464,12 +467,12 @@ __device__ __forceinline__ int node_class(const RArgs& a, unsigned q) {
 template <bool INIT>
 __global__ void __launch_bounds__(VT, 3) k_cg_r_update(const RArgs a) {
   __shared__ double sm[kFinishSmem];
-  __shared__ double tab[16];
+  __shared__ double tab[2 * kClsPerField];
   __shared__ double spre[kPreScalars];
   __shared__ unsigned long long seq_pre;
   __shared__ int last_flag;
   pdl_launch_dependents();
-  if (threadIdx.x < 16) tab[threadIdx.x] = (threadIdx.x < 8 * a.nf) ? a.dtab[threadIdx.x] : 1.0;   // per-solve constant
+  if (threadIdx.x < 2 * kClsPerField) tab[threadIdx.x] = (threadIdx.x < kClsPerField * a.nf) ? a.dtab[threadIdx.x] : 1.0;   // per-solve constant
   pdl_wait();
   if (!INIT && a.S[S_REASON] != 0.0) return;
   if (a.fold.enabled) {   // snapshot for the epilogue (cg_device.cuh: apply_post / finish_reduction)
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(VT, 3) k_cg_r_update(const RArgs a) {
   const int f = blockIdx.y;
   double* rf = a.r + (long long)f * a.field;
   const double* wf = INIT ? nullptr : a.w + (long long)f * a.field;
-  const double* tf = tab + f * 8;
+  const double* tf = tab + f * kClsPerField;
   const bool zc = a.zero_class[f] != 0;
   const bool xdim = a.ni > 1;
   double srz = 0.0, szz = 0.0;
@@ -509,17 +512,18 @@ __global__ void __launch_bounds__(VT, 3) k_cg_r_update(const RArgs a) {
   };
   auto classes = [&](int& c0, int& c1) {
     const int bx = (xdim && ((i == 0 && a.dom_lo) || (i == a.ni - 1 && a.dom_hi))) ? 4 : 0;
-    const int bxy = bx + ((j == 0 || j == a.nj - 1) ? 2 : 0);
-    c0 = bxy + ((k == 0 || k == a.nk - 1) ? 1 : 0);
-    c1 = bxy + ((k + 1 == a.nk - 1) ? 1 : 0);
+    int bxy = bx + ((j == 0 || j == a.nj - 1) ? 2 : 0);
+    if (a.q2) bxy += (int)((((i & 1u) << 2) | ((j & 1u) << 1)) << 3);   // mid-node parities of the row
+    c0 = bxy + ((k == 0 || k == a.nk - 1) ? 1 : 0) + (a.q2 ? (int)((k & 1u) << 3) : 0);
+    c1 = bxy + ((k + 1 == a.nk - 1) ? 1 : 0) + (a.q2 ? (int)(((k + 1) & 1u) << 3) : 0);
   };
   auto one = [&](long long qq, double2 rv, double2 wv) {
     int c0, c1;
     classes(c0, c1);
     double2 rn = rv;
     if (!INIT) {
-      rn.x = (zc && c0) ? 0.0 : fma(-alpha, wv.x, rv.x);
-      rn.y = (zc && c1) ? 0.0 : fma(-alpha, wv.y, rv.y);
+      rn.x = (zc && (c0 & 7)) ? 0.0 : fma(-alpha, wv.x, rv.x);
+      rn.y = (zc && (c1 & 7)) ? 0.0 : fma(-alpha, wv.y, rv.y);
       *reinterpret_cast<double2*>(rf + qq) = rn;
       push_halo2(a, f, qq, rn);
     }
@@ -705,7 +709,7 @@ __global__ void __launch_bounds__(VT) k_classify_mask(RArgs a, const uint8_t* __
   for (long long n = (long long)blockIdx.x * VT + threadIdx.x; n < n_nodes; n += (long long)gridDim.x * VT) {
     const unsigned row = (unsigned)(((unsigned long long)(unsigned)n * mag_nk) >> sh_nk);
     const unsigned k = (unsigned)n - row * nk_u;
-    const int cls = node_class(a, row * a.pitch + k);
+    const int cls = node_class(a, row * a.pitch + k) & 7;
     const bool m = mask[n] != 0;
     c0 += (m && cls == 0);
     c1 += (!m && cls != 0);
@@ -717,26 +721,345 @@ __global__ void __launch_bounds__(VT) k_classify_mask(RArgs a, const uint8_t* __
 // reciprocal diagonal per boundary class; same expression as k_diag_structured (apply_structured.cu)
 __global__ void k_dinv_table(GridDesc g, Coef c, int nf, int jacobi, int zc0, int zc1, double* __restrict__ tab) {
   const int t = threadIdx.x;
-  if (t >= 8 * nf) return;
+  if (t >= kClsPerField * nf) return;
+  const int f = t / kClsPerField, cls = t % kClsPerField;
+  const int bnd = cls & 7, par = cls >> 3;
   // full-boundary Dirichlet field: every boundary class is a constrained row -> z = 0, p = 0 there
-  if (((t >> 3) ? zc1 : zc0) && (t & 7)) { tab[t] = 0.0; return; }
+  if ((f ? zc1 : zc0) && bnd) { tab[t] = 0.0; return; }
   if (!jacobi) { tab[t] = 1.0; return; }
-  const int f = t >> 3, bx = (t >> 2) & 1, by = (t >> 1) & 1, bz = t & 1;
-  // centre entries: row 0 of the assembled 1-D matrices is a domain-boundary row; on a uniform axis an
-  // interior row's centre entry is exactly twice that (two cells instead of one); dummy axis: M=[1], K=[0]
-  const int b[3] = {bx, by, bz};
+  // centre entries of the assembled 1-D matrices on a uniform axis.  Degree 1: row 0 is a domain-boundary row,
+  // an interior row's centre entry is exactly twice that (two cells instead of one).  Degree 2 (band 2): row 0 =
+  // boundary vertex, row 1 = mid node, an interior vertex again twice row 0.  Dummy axis: M = [1], K = [0].
+  const int w = 2 * g.band + 1;
   double m[3], k[3];
   for (int a = 0; a < 3; ++a) {
-    const double mb = g.m1d[a][1], kb = g.k1d[a][1];
+    const int b = (bnd >> (2 - a)) & 1, odd = (par >> (2 - a)) & 1;
     const bool dummy = g.n[a] == 1;
-    m[a] = (b[a] || dummy) ? mb : 2.0 * mb;
-    k[a] = (b[a] || dummy) ? kb : 2.0 * kb;
+    const double mb = g.m1d[a][g.band], kb = g.k1d[a][g.band];
+    if (dummy) { m[a] = mb; k[a] = kb; }
+    else if (g.band == 2 && odd) { m[a] = g.m1d[a][w + g.band]; k[a] = g.k1d[a][w + g.band]; }
+    else { m[a] = b ? mb : 2.0 * mb; k[a] = b ? kb : 2.0 * kb; }
   }
   const double mxc = m[0], kxc = k[0], myc = m[1], kyc = k[1], mzc = m[2], kzc = k[2];
   const double K = kxc * myc * mzc + mxc * kyc * mzc + mxc * myc * kzc;
   const double M = mxc * myc * mzc;
   const double d = c.cK[f][f] * K + c.cM[f][f] * M;
   tab[t] = 1.0 / d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Degree 2 (BASELINE configs[3]: Q2 192^3 block Picard): the same two-kernel iteration on the padded layout.
+// k_cg_fused_apply_q2 = the uniform-grid Q2 stencil of apply_structured_q2.cu (node pairs along z, 16-byte shared
+// loads, constant vertex / mid rows, shifting 5-plane queue along x) with the CG prologue fused in: planes of r and
+// p_old stream through a cp.async ring (16-byte copies: the padded rows are 16-byte aligned; zero-filled outside
+// the domain), p = D^-1 r + beta p_old is formed in shared memory over the whole halo'd tile (the reciprocal
+// diagonal comes from the 64-entry class table: node parity x boundary per axis), p is stored into the direction
+// ring (ghost planes included) and w = A p, <p, w> follow from the tile.  x is always deferred (section 4.6): the
+// r-update kernel of the Q1 path serves Q2 unchanged (class index extended by the parity bits).
+// Passes per iteration: r, p_old in; p, w out (4) + r-update 3 + x 17/15 = 8.13, against 13 + reciprocal diagonal
+// for the unfused sequence this replaces.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int Q2K = 32, Q2J = 8, Q2H = 2, Q2ROW = Q2K + 2 * Q2H, Q2SLOT = (Q2J + 2 * Q2H) * Q2ROW, Q2RING = 3;
+constexpr int Q2PT = 16, Q2NT = Q2PT * Q2J;     // 16 pair-threads per row, 128 threads
+
+struct AxisQ2 {     // assembled 1-D rows on an equally spaced axis; [0] interior, [1] domain-boundary centre
+  double mV2, mV1, mVc[2], mM1, mMc;
+  double kV2, kV1, kVc[2], kM1, kMc;
+};
+
+struct Q2FArgs {
+  int n[3];
+  int pitch;
+  long long plane, field;
+  AxisQ2 ax[3];
+  const double* r;
+  const double* pin;
+  double* pout;
+  double* w;
+  Coef c;
+  double* dot_partials;
+  int i_begin, i_end;
+  int ntj, ntk, nseg;
+  int dom_lo, dom_hi;
+  const double* S;
+  const double* dtab;
+  FoldArgs fold;
+};
+
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr, bool valid) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.eq.u32 p, %2, 0;\n cp.async.cg.shared.global [%0], [%1], 16, p;\n}\n" ::"r"(smem_addr),
+      "l"(gptr), "r"((unsigned)valid)
+      : "memory");
+}
+
+template <int NF>
+struct __align__(16) SmemQ2 {
+  double r[Q2RING][NF][Q2SLOT];
+  double p[Q2RING][NF][Q2SLOT];
+  double dtab[2 * kClsPerField];
+  double red[Q2NT / 32];
+  double fin[kFinishSmem];
+  double spre[kPreScalars];
+  unsigned long long seq_pre;
+  int last_flag;
+};
+
+template <int NF>
+__global__ void __launch_bounds__(Q2NT, 3) k_cg_fused_apply_q2(const Q2FArgs s) {
+  extern __shared__ __align__(16) unsigned char smem_raw_q2[];
+  SmemQ2<NF>& sm = *reinterpret_cast<SmemQ2<NF>*>(smem_raw_q2);
+  const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  if (tid < 2 * kClsPerField) sm.dtab[tid] = tid < kClsPerField * NF ? s.dtab[tid] : 1.0;   // per-solve constant
+  pdl_wait();   // everything below reads what the previous kernel of the stream produced
+  if (s.S[S_REASON] != 0.0) return;
+  if (s.fold.enabled) {
+    if (tid < kPreScalars) sm.spre[tid] = s.fold.S[tid];
+    if (tid == kPreScalars && s.fold.ipc.world > 1) sm.seq_pre = *s.fold.ipc.seq_dev;
+  }
+  const double beta = (s.S[S_ITS] == 0.0) ? 0.0 : s.S[S_RZ] / s.S[S_RZ_OLD];
+
+  const int ni = s.n[0], nj = s.n[1], nk = s.n[2], pitch = s.pitch;
+  const int ntiles = s.ntj * s.ntk;
+  const int tile = blockIdx.x % ntiles, seg = blockIdx.x / ntiles;
+  const int tkid = tile % s.ntk, tjid = tile / s.ntk;
+  const int k0 = tkid * Q2K, j0 = tjid * Q2J;            // even: node parity = local parity
+  const int nown = s.i_end - s.i_begin;
+  const int i_lo = s.i_begin + bstart(seg, nown, s.nseg);
+  const int i_hi = s.i_begin + bstart(seg + 1, nown, s.nseg);
+  const int warp = tid >> 5, lane = tid & 31;
+  const int jr = warp + 4 * (lane >> 4);               // rows {w, w + 4} of a warp have one parity
+  const int kp = 2 * (lane & 15);
+  const int j = j0 + jr, k = k0 + kp;
+  const bool rowV = (jr & 1) == 0;
+  const bool actV = (j < nj) && (k < nk), actM = (j < nj) && (k + 1 < nk);
+  const long long plane = s.plane;
+  // planes whose p this run stores: its own planes plus the ghost planes next to the first / last owned one
+  const int pw_lo = (i_lo == s.i_begin && s.i_begin > 0) ? i_lo - Q2H : i_lo;
+  const int pw_hi = (i_hi == s.i_end && s.i_end < ni) ? i_hi + 1 : i_hi;
+
+  // copy / combine duties (fixed across planes): 16-byte pairs tid + q * Q2NT of a slot
+  constexpr int NPAIR = Q2SLOT / 2, NDUTY = (NPAIR + Q2NT - 1) / Q2NT;
+  long long coff[NDUTY];
+  bool cok[NDUTY];
+  int ccls[NDUTY][2];      // class bits of the two elements that do not depend on the plane
+#pragma unroll
+  for (int q = 0; q < NDUTY; ++q) {
+    const int e = 2 * (tid + q * Q2NT);
+    const int rr = e / Q2ROW, cc = e - rr * Q2ROW;
+    const int jj = j0 - Q2H + rr, kk = k0 - Q2H + cc;
+    cok[q] = (e < Q2SLOT) && (jj >= 0) && (jj < nj) && (kk >= 0) && (kk < pitch);
+    coff[q] = cok[q] ? (long long)jj * pitch + kk : 0;
+    const int by = (jj == 0 || jj == nj - 1) ? 2 : 0, py = (jj & 1) << 1;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int kq = kk + u;
+      const int bz = (kq == 0 || kq == nk - 1) ? 1 : 0, pz = kq & 1;
+      ccls[q][u] = ((py | pz) << 3) | by | bz;
+    }
+  }
+  const unsigned sr_base = (unsigned)__cvta_generic_to_shared(&sm.r[0][0][0]);
+  const unsigned sp_base = (unsigned)__cvta_generic_to_shared(&sm.p[0][0][0]);
+
+  const AxisQ2& ay = s.ax[1];
+  const AxisQ2& az = s.ax[2];
+  const int jb = (j == 0 || j == nj - 1) ? 1 : 0, kb = (k == 0 || k == nk - 1) ? 1 : 0;
+  const double myVc = ay.mVc[jb], kyVc = ay.kVc[jb], mzVc = az.mVc[kb], kzVc = az.kVc[kb];
+
+  double qcV[NF][5], qdV[NF][5], qcM[NF][5], qdM[NF][5], cenV[NF][3], cenM[NF][3];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+#pragma unroll
+    for (int d = 0; d < 5; ++d) qcV[f][d] = qdV[f][d] = qcM[f][d] = qdM[f][d] = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) cenV[f][d] = cenM[f][d] = 0.0;
+  }
+  double dot = 0.0;
+  const int i_first = i_lo - Q2H;
+  const long long own = (long long)j * pitch + k;
+
+  auto issue = [&](int pl, int slot) {
+    const bool in = (unsigned)pl < (unsigned)ni;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const long long base = (long long)f * s.field + (long long)(in ? pl : 0) * plane;
+#pragma unroll
+      for (int q = 0; q < NDUTY; ++q)
+        if (2 * (tid + q * Q2NT) < Q2SLOT) {
+          const unsigned off = (unsigned)(((slot * NF + f) * Q2SLOT + 2 * (tid + q * Q2NT)) * 8);
+          cp_async16(sr_base + off, s.r + base + coff[q], in && cok[q]);
+          cp_async16(sp_base + off, s.pin + base + coff[q], in && cok[q]);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+#define DPP_Q2F_ROW(T, MYR, KYR)                                                                      \
+  {                                                                                                   \
+    const double2 p0 = *reinterpret_cast<const double2*>(T);                                          \
+    const double2 p1 = *reinterpret_cast<const double2*>((T) + 2);                                    \
+    const double2 p2 = *reinterpret_cast<const double2*>((T) + 4);                                    \
+    const double s2 = p0.x + p2.x, s1 = p0.y + p1.y, sm_ = p1.x + p2.x;                               \
+    const double tzV = fma(az.mV2, s2, fma(az.mV1, s1, mzVc * p1.x));                                 \
+    const double uzV = fma(az.kV2, s2, fma(az.kV1, s1, kzVc * p1.x));                                 \
+    const double tzM = fma(az.mM1, sm_, az.mMc * p1.y);                                               \
+    const double uzM = fma(az.kM1, sm_, az.kMc * p1.y);                                               \
+    cV = fma(MYR, tzV, cV);                                                                           \
+    dV = fma(KYR, tzV, fma(MYR, uzV, dV));                                                            \
+    cM = fma(MYR, tzM, cM);                                                                           \
+    dM = fma(KYR, tzM, fma(MYR, uzM, dM));                                                            \
+  }
+
+  __syncthreads();   // dtab, spre
+  issue(i_first, 0);
+  issue(i_first + 1, 1);
+  int slot = 0;
+  const int i_last = i_hi + Q2H - 1;
+#pragma unroll 1
+  for (int ip = i_first; ip <= i_last; ++ip) {
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    __syncthreads();
+    {
+      int nslot = slot + 2;
+      if (nslot >= Q2RING) nslot -= Q2RING;
+      issue(ip + 2, nslot);
+    }
+    const bool in = (unsigned)ip < (unsigned)ni;
+    // ---- p = D^-1 r + beta p_old over the halo'd tile, in place (zero-filled elements stay zero)
+    if (in) {
+      const int cx = ((ip & 1) << 5) | (((ni > 1) && ((ip == 0 && s.dom_lo) || (ip == ni - 1 && s.dom_hi))) ? 4 : 0);
+#pragma unroll
+      for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int q = 0; q < NDUTY; ++q)
+          if (2 * (tid + q * Q2NT) < Q2SLOT) {
+            const int e = 2 * (tid + q * Q2NT);
+            double2 pv = *reinterpret_cast<double2*>(&sm.p[slot][f][e]);
+            const double2 rv = *reinterpret_cast<const double2*>(&sm.r[slot][f][e]);
+            pv.x = fma(beta, pv.x, sm.dtab[f * kClsPerField + (cx | ccls[q][0])] * rv.x);
+            pv.y = fma(beta, pv.y, sm.dtab[f * kClsPerField + (cx | ccls[q][1])] * rv.y);
+            *reinterpret_cast<double2*>(&sm.p[slot][f][e]) = pv;
+          }
+    }
+    __syncthreads();
+    const bool pwr = in && ip >= pw_lo && ip < pw_hi;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      double cV = 0.0, dV = 0.0, cM = 0.0, dM = 0.0, xcV = 0.0, xcM = 0.0;
+      if (in && actV) {
+        const double* t = &sm.p[slot][f][jr * Q2ROW + kp];
+        if (rowV) {
+          DPP_Q2F_ROW(t, ay.mV2, ay.kV2)
+          DPP_Q2F_ROW(t + Q2ROW, ay.mV1, ay.kV1)
+          DPP_Q2F_ROW(t + 2 * Q2ROW, myVc, kyVc)
+          DPP_Q2F_ROW(t + 3 * Q2ROW, ay.mV1, ay.kV1)
+          DPP_Q2F_ROW(t + 4 * Q2ROW, ay.mV2, ay.kV2)
+        } else {
+          DPP_Q2F_ROW(t + Q2ROW, ay.mM1, ay.kM1)
+          DPP_Q2F_ROW(t + 2 * Q2ROW, ay.mMc, ay.kMc)
+          DPP_Q2F_ROW(t + 3 * Q2ROW, ay.mM1, ay.kM1)
+        }
+        xcV = t[2 * Q2ROW + 2];
+        xcM = t[2 * Q2ROW + 3];
+        if (pwr) {   // the direction of this iteration, for the next one and for the deferred x update
+          double* po = s.pout + (long long)f * s.field + (long long)ip * plane + own;
+          if (actM) *reinterpret_cast<double2*>(po) = make_double2(xcV, xcM);
+          else po[0] = xcV;
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        qcV[f][d] = qcV[f][d + 1]; qdV[f][d] = qdV[f][d + 1];
+        qcM[f][d] = qcM[f][d + 1]; qdM[f][d] = qdM[f][d + 1];
+      }
+      qcV[f][4] = cV; qdV[f][4] = dV; qcM[f][4] = cM; qdM[f][4] = dM;
+      cenV[f][0] = cenV[f][1]; cenV[f][1] = cenV[f][2]; cenV[f][2] = xcV;
+      cenM[f][0] = cenM[f][1]; cenM[f][1] = cenM[f][2]; cenM[f][2] = xcM;
+    }
+    const int io = ip - Q2H;
+    if (actV && io >= i_lo && io < i_hi) {
+      const AxisQ2& axx = s.ax[0];
+      double KxV[NF], MxV[NF], KxM[NF], MxM[NF];
+      if ((io & 1) == 0) {
+        const int xb = ((io == 0 && s.dom_lo) || (io == ni - 1 && s.dom_hi)) ? 1 : 0;
+        const double mc = axx.mVc[xb], kc = axx.kVc[xb];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          const double c2 = qcV[f][0] + qcV[f][4], c1 = qcV[f][1] + qcV[f][3], c0 = qcV[f][2];
+          const double d2 = qdV[f][0] + qdV[f][4], d1 = qdV[f][1] + qdV[f][3], d0 = qdV[f][2];
+          MxV[f] = fma(axx.mV2, c2, fma(axx.mV1, c1, mc * c0));
+          KxV[f] = fma(axx.kV2, c2, fma(axx.kV1, c1, fma(kc, c0, fma(axx.mV2, d2, fma(axx.mV1, d1, mc * d0)))));
+          const double e2 = qcM[f][0] + qcM[f][4], e1 = qcM[f][1] + qcM[f][3], e0 = qcM[f][2];
+          const double g2 = qdM[f][0] + qdM[f][4], g1 = qdM[f][1] + qdM[f][3], g0 = qdM[f][2];
+          MxM[f] = fma(axx.mV2, e2, fma(axx.mV1, e1, mc * e0));
+          KxM[f] = fma(axx.kV2, e2, fma(axx.kV1, e1, fma(kc, e0, fma(axx.mV2, g2, fma(axx.mV1, g1, mc * g0)))));
+        }
+      } else {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          const double c1 = qcV[f][1] + qcV[f][3], c0 = qcV[f][2], d1 = qdV[f][1] + qdV[f][3], d0 = qdV[f][2];
+          MxV[f] = fma(axx.mM1, c1, axx.mMc * c0);
+          KxV[f] = fma(axx.kM1, c1, fma(axx.kMc, c0, fma(axx.mM1, d1, axx.mMc * d0)));
+          const double e1 = qcM[f][1] + qcM[f][3], e0 = qcM[f][2], g1 = qdM[f][1] + qdM[f][3], g0 = qdM[f][2];
+          MxM[f] = fma(axx.mM1, e1, axx.mMc * e0);
+          KxM[f] = fma(axx.kM1, e1, fma(axx.kMc, e0, fma(axx.mM1, g1, axx.mMc * g0)));
+        }
+      }
+      const long long node = (long long)io * plane + own;
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        double yV = 0.0, yM = 0.0;
+#pragma unroll
+        for (int g = 0; g < NF; ++g) {
+          yV = fma(s.c.cK[f][g], KxV[g], yV);
+          yV = fma(s.c.cM[f][g], MxV[g], yV);
+          yM = fma(s.c.cK[f][g], KxM[g], yM);
+          yM = fma(s.c.cM[f][g], MxM[g], yM);
+        }
+        double* wo = s.w + (long long)f * s.field + node;
+        dot = fma(cenV[f][0], yV, dot);
+        if (actM) {
+          *reinterpret_cast<double2*>(wo) = make_double2(yV, yM);
+          dot = fma(cenM[f][0], yM, dot);
+        } else {
+          wo[0] = yV;
+        }
+      }
+    }
+    if (++slot == Q2RING) slot = 0;
+  }
+#undef DPP_Q2F_ROW
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+
+  if (s.dot_partials != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) sm.red[warp] = dot;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < Q2NT / 32; ++w) t += sm.red[w];
+      s.dot_partials[blockIdx.x] = t;
+    }
+    if (s.fold.enabled && last_block_arrives(s.fold.counter, gridDim.x, &sm.last_flag))
+      finish_reduction<Q2NT>(s.dot_partials, (int)gridDim.x, 1, s.fold.S, s.fold.hist, s.fold.post, 0, s.fold.ipc, sm.fin,
+                             s.fold.ipc.ll == 3, FoldPre{sm.spre, &sm.seq_pre}, s.fold.xring);
+  }
+}
+
+AxisQ2 axis_q2(int n_nodes, double h) {
+  AxisQ2 a{};
+  if (n_nodes == 1) {   // dummy axis of a 2-D mesh: M = [1], K = [0]
+    a.mVc[0] = a.mVc[1] = 1.0;
+    a.mMc = 1.0;
+    return a;
+  }
+  const double b = h / 30.0, q = 1.0 / (3.0 * h);
+  a.mV2 = -b; a.mV1 = 2 * b; a.mVc[0] = 8 * b; a.mVc[1] = 4 * b; a.mM1 = 2 * b; a.mMc = 16 * b;
+  a.kV2 = q; a.kV1 = -8 * q; a.kVc[0] = 14 * q; a.kVc[1] = 7 * q; a.kM1 = -8 * q; a.kMc = 16 * q;
+  return a;
 }
 
 void magic_div(unsigned d, unsigned long long* mag, unsigned* sh) {
@@ -805,11 +1128,25 @@ void cg_fused_destroy(dpp_context* ctx) {
   ctx->fused = nullptr;
 }
 
-bool cg_fused_available(const dpp_context* ctx, int nf, int operator_mode, int pc_type) {
-  return ctx->family == DPP_KERNEL_STRUCTURED && ctx->grid.band == 1 && ctx->grid_uniform && !ctx->force_table_kernel &&
-         !ctx->fused_cg_disabled &&
-         operator_mode == DPP_OP_MATRIX_FREE && (pc_type == DPP_PC_NONE || pc_type == DPP_PC_JACOBI) &&
-         (nf == 1 || nf == 2) && getenv("DPP_NO_FUSED_CG") == nullptr && encode_fn() != nullptr;
+static int fused_state(dpp_context* ctx, FusedState** out);
+static int ring_state(dpp_context* ctx, FusedState* F);
+
+// degree 2: single-GPU handles only (the slab halo of the padded residual is two planes wide on the lower side and
+// still goes through the unfused sequence), and only with the direction ring (the kernel has no in-kernel x update)
+static bool q2_fused_usable(dpp_context* ctx) {
+  if (ctx->world != 1 || getenv("DPP_NO_FUSED_Q2") != nullptr) return false;
+  FusedState* F = nullptr;
+  if (fused_state(ctx, &F) != DPP_OK) { ctx->err.clear(); cudaGetLastError(); return false; }
+  return ring_state(ctx, F) == DPP_OK;
+}
+
+bool cg_fused_available(dpp_context* ctx, int nf, int operator_mode, int pc_type) {
+  const bool common = ctx->family == DPP_KERNEL_STRUCTURED && !ctx->force_table_kernel && !ctx->fused_cg_disabled && operator_mode == DPP_OP_MATRIX_FREE &&
+                      (pc_type == DPP_PC_NONE || pc_type == DPP_PC_JACOBI) && (nf == 1 || nf == 2) &&
+                      getenv("DPP_NO_FUSED_CG") == nullptr;
+  if (!common) return false;
+  if (ctx->grid.band == 1) return ctx->grid_uniform && encode_fn() != nullptr;
+  return ctx->grid.band == 2 && ctx->q2_uniform && q2_fused_usable(ctx);
 }
 
 static PadGeom pad_geom(const dpp_context* ctx, const FusedState* F, int nf) {
@@ -855,7 +1192,7 @@ static int fused_state(dpp_context* ctx, FusedState** out) {
       DPP_CHECK(dev_alloc(ctx, &b, 2 * F->field));
       DPP_CUDA(cudaMemsetAsync(b, 0, sizeof(double) * 2 * F->field, ctx->stream));
     }
-    for (int nf = 1; nf <= 2; ++nf) {
+    for (int nf = 1; nf <= 2 && g.band == 1; ++nf) {
       DPP_CHECK(make_map(ctx, F, &F->tm[nf - 1][0], F->buf[0], nf, true));
       DPP_CHECK(make_map(ctx, F, &F->tm[nf - 1][1], F->buf[1], nf, true));
       DPP_CHECK(make_map(ctx, F, &F->tm[nf - 1][2], F->buf[2], nf, true));
@@ -890,7 +1227,7 @@ static int ring_state(dpp_context* ctx, FusedState* F) {
     }
     DPP_CUDA(cudaMemsetAsync(F->pring[j], 0, sizeof(double) * 2 * F->field, ctx->stream));
   }
-  for (int nf = 1; nf <= 2; ++nf)
+  for (int nf = 1; nf <= 2 && ctx->grid.band == 1; ++nf)
     for (int j = 0; j < kXRing; ++j) DPP_CHECK(make_map(ctx, F, &F->tmr[nf - 1][j], F->pring[j], nf, true));
   DPP_CHECK(dev_alloc(ctx, &F->d_xring, 2 * kXRing));
   DPP_CUDA(cudaMemsetAsync(F->d_xring, 0, sizeof(double) * 2 * kXRing, ctx->stream));
@@ -900,7 +1237,7 @@ static int ring_state(dpp_context* ctx, FusedState* F) {
 
 // decided at the start of every solve / timing run (cg_fused_table) and read by all launches of that solve
 static void decide_defer_x(dpp_context* ctx, FusedState* F) {
-  const bool want = (ctx->world == 1 || comm_ipc_ready(ctx)) && getenv("DPP_NO_DEFER_X") == nullptr;
+  const bool want = (ctx->world == 1 || comm_ipc_ready(ctx)) && (getenv("DPP_NO_DEFER_X") == nullptr || ctx->grid.band == 2);
   F->defer = want && ring_state(ctx, F) == DPP_OK;
 }
 
@@ -1026,6 +1363,54 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
   return DPP_OK;
 }
 
+// degree 2: iteration kernel on the padded layout (always with the direction ring)
+static int launch_apply_q2(dpp_context* ctx, FusedState* F, int nf, const Coef& c, const double* pin, double* pout,
+                           int slot, const double* dtab, int* n_partial_blocks) {
+  const GridDesc& g = ctx->grid;
+  const long long uplane = (long long)g.n[1] * g.n[2];
+  Q2FArgs s{};
+  for (int d = 0; d < 3; ++d) {
+    s.n[d] = g.n[d];
+    s.ax[d] = axis_q2(g.n[d], ctx->uni_h[d]);
+  }
+  s.pitch = F->pitch; s.plane = F->plane; s.field = F->field;
+  s.r = F->buf[0]; s.pin = pin; s.pout = pout; s.w = F->buf[3];
+  s.c = c;
+  s.dot_partials = ctx->d_partials;
+  s.i_begin = (int)(ctx->owned_begin / uplane);
+  s.i_end = (int)(ctx->owned_end / uplane);
+  s.S = ctx->d_scalars + (size_t)slot * S_SLOT_SIZE;
+  s.dtab = dtab;
+  s.dom_lo = ctx->dom_lo; s.dom_hi = ctx->dom_hi;
+  s.fold = fold_args(ctx, slot, POST_CG_PAP, 0);
+  s.fold.xring = F->d_xring;
+  s.ntk = (g.n[2] + Q2K - 1) / Q2K;
+  s.ntj = (g.n[1] + Q2J - 1) / Q2J;
+  const int tiles = s.ntk * s.ntj;
+  const int nown = s.i_end - s.i_begin;
+  if (nown <= 0) { *n_partial_blocks = 0; return DPP_OK; }
+  if (tiles > kMaxPartialBlocks) {
+    ctx->set_error("fused CG (degree 2): plane too wide for the partials scratch");
+    return DPP_ERR_INVALID;
+  }
+  s.nseg = choose_x_segments(tiles, nown, ctx->sm_count * 3, kMaxPartialBlocks, 2 * Q2H);
+  if (const char* e = getenv("DPP_FUSED_SCHED"))
+    if (atoi(e) > 0 && (long long)tiles * atoi(e) <= kMaxPartialBlocks) s.nseg = std::min(atoi(e), nown);
+  static bool attr = false;
+  if (!attr) {
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<2>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<1>)));
+    attr = true;
+  }
+  const dim3 grid(tiles * s.nseg), block(Q2NT);
+  if (nf == 2) DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<2>, grid, block, sizeof(SmemQ2<2>), ctx->stream, s));
+  else DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<1>, grid, block, sizeof(SmemQ2<1>), ctx->stream, s));
+  ctx->launches++;
+  DPP_CUDA(cudaGetLastError());
+  *n_partial_blocks = (int)grid.x;
+  return DPP_OK;
+}
+
 // is the Dirichlet set of mask field `fl` exactly the set of domain-boundary nodes?  (decided once per BC
 // change with a device pass over the mask; then boundary classes double as the row/column mask)
 static int classify_bcs(dpp_context* ctx, FusedState* F, int fl, const RArgs& geom) {
@@ -1067,6 +1452,7 @@ static int make_rargs(dpp_context* ctx, FusedState* F, int nf, int slot, const d
   magic_div(a.nj, &a.mag_j, &a.sh_j);
   a.dom_lo = ctx->dom_lo;
   a.dom_hi = ctx->dom_hi;
+  a.q2 = ctx->grid.band == 2 ? 1 : 0;
   a.plane = F->plane;
   a.halo = comm_ipc_halo(ctx);
   if (fld != nullptr) {
@@ -1108,7 +1494,7 @@ int cg_fused_table(dpp_context* ctx, const Coef& c, int nf, int pc_type, const i
   decide_defer_x(ctx, F);
   RArgs geom{};
   DPP_CHECK(make_rargs(ctx, F, nf, 0, d_tab, &geom, fld));
-  k_dinv_table<<<1, 16, 0, ctx->stream>>>(ctx->grid, c, nf, pc_type == DPP_PC_JACOBI ? 1 : 0, geom.zero_class[0],
+  k_dinv_table<<<1, 2 * kClsPerField, 0, ctx->stream>>>(ctx->grid, c, nf, pc_type == DPP_PC_JACOBI ? 1 : 0, geom.zero_class[0],
                                           nf == 2 ? geom.zero_class[1] : 0, d_tab);
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
@@ -1175,12 +1561,20 @@ int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const 
   const bool defer = F->defer;
   // classic: p ping-pongs between two buffers; deferred x: iteration `it` reads ring buffer it % 16 (p_{it-1}) and
   // writes (it + 1) % 16 (p_it), so the last fifteen directions are still there when x is brought up to date
-  const CUtensorMap& tm_pin = defer ? F->tmr[nf - 1][it % kXRing] : F->tm[nf - 1][1 + (int)(it & 1)];
   double* pout_buf = defer ? F->pring[(it + 1) % kXRing] : F->buf[1 + (int)((it + 1) & 1)];
   bool all_class_masked = true;
   for (int f = 0; f < nf; ++f) all_class_masked = all_class_masked && F->bc_full_gen[fld[f]] == ctx->bc_gen[fld[f]] && F->bc_full[fld[f]];
   int nb = 0;
-  DPP_CHECK(launch_apply(ctx, F, nf, true, c, tm_pin, pout_buf, slot, dtab, true, &nb, all_class_masked, defer));
+  if (ctx->grid.band == 2) {
+    if (!defer) {
+      ctx->set_error("fused CG (degree 2) needs the direction ring");
+      return DPP_ERR_INVALID;
+    }
+    DPP_CHECK(launch_apply_q2(ctx, F, nf, c, F->pring[it % kXRing], pout_buf, slot, dtab, &nb));
+  } else {
+    const CUtensorMap& tm_pin = defer ? F->tmr[nf - 1][it % kXRing] : F->tm[nf - 1][1 + (int)(it & 1)];
+    DPP_CHECK(launch_apply(ctx, F, nf, true, c, tm_pin, pout_buf, slot, dtab, true, &nb, all_class_masked, defer));
+  }
   if (!(ctx->world == 1 || comm_ipc_ready(ctx))) DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
   if (all_class_masked) return DPP_OK;   // constrained rows never leave zero: no row fix-up needed
   // row elimination: w = p on constrained rows (identity rows of A_bc)

@@ -164,7 +164,7 @@ int dpp_create(dpp_handle* h, int device, int dim, int degree, int64_t n_nodes, 
     DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_partials, (int64_t)dpp::kMaxPartialBlocks * dpp::kMaxDotWidth));
     DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_scalars, dpp::kNumScalars));
     DPP_CUDA(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * dpp::kNumScalars, ctx->stream));
-    DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_dtab, 32));
+    DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_dtab, 2 * 128));
     DPP_CHECK(dpp::dev_alloc(ctx, &ctx->d_counters, 4));
     DPP_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned) * 4, ctx->stream));
     DPP_CUDA(cudaMallocHost((void**)&ctx->h_scalars, sizeof(double) * dpp::kNumScalars));

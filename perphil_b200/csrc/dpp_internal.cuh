@@ -94,6 +94,8 @@ struct dpp_context {
   double* d_tables = nullptr;     // backing store of grid.m1d/k1d
   std::vector<double> h_axis[3];  // 1-D vertex coordinates per axis (structured)
   bool grid_uniform = false;      // equal spacing on every axis -> apply_structured_uniform.cu
+  bool q2_uniform = false;        // degree 2 lattice with equal cell size on every axis (uni_h)
+  double uni_h[3] = {1.0, 1.0, 1.0};
   bool force_table_kernel = false;
   bool fused_cg_disabled = false;   // dpp_set_fused_cg(h, 0): ranks of a slab run agree on ONE protocol
   double uni_m_off[3] = {0, 0, 0}, uni_k_off[3] = {0, 0, 0};
@@ -143,7 +145,7 @@ struct dpp_context {
   double* d_scalars = nullptr;    // device scalar block
   double* h_scalars = nullptr;    // pinned mirror
   unsigned* d_counters = nullptr; // arrival counters of the folded reductions [4]
-  double* d_dtab = nullptr;       // [2 slots][16] reciprocal-diagonal class tables of the fused CG
+  double* d_dtab = nullptr;       // [2 slots][2 fields][64] reciprocal-diagonal class tables of the fused CG
   double* d_hist[2] = {nullptr, nullptr};  // residual history per solver slot
   int hist_cap[2] = {0, 0};
 

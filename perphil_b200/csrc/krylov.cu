@@ -232,7 +232,7 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
   if (fused && op.kind == 0 && cg_fused_available(ctx, op.nf, op.mode, pc.type)) {
     // two kernels per iteration (cg_fused_uniform.cu): p, x updates live inside the apply kernel
     const Coef coef = op.nf == 2 ? dpp_coef(ctx) : block_coef(ctx, op.row, op.col);
-    double* dtab = ctx->d_dtab + (size_t)slot * 16;
+    double* dtab = ctx->d_dtab + (size_t)slot * 128;
     const int fld[2] = {op.nf == 2 ? 0 : op.row, 1};
     DPP_CHECK(cg_fused_table(ctx, coef, op.nf, pc.type, fld, dtab));
     DPP_CHECK(cg_fused_begin(ctx, op.nf, b));
@@ -985,7 +985,12 @@ int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply
       if (i == 0) DPP_CUDA(cudaEventRecord(e0, ctx->stream));
       if (pass == 0) DPP_CHECK(cg_fused_apply(ctx, 2, coef, i + warmup, fld, slot, dtab));
       else if (pass == 1) DPP_CHECK(cg_fused_r_update(ctx, 2, fld, slot, dtab));
-      else DPP_CHECK(cg_fused_plain_apply(ctx, 2, coef, true, &nb));
+      else if (ctx->grid.band == 1) DPP_CHECK(cg_fused_plain_apply(ctx, 2, coef, true, &nb));
+      else {   // degree 2: the stand-alone stencil kernel on the C-ABI layout (apply_structured_q2.cu)
+        OpSpec op{};
+        op.nf = 2; op.mode = DPP_OP_MATRIX_FREE; op.premasked = 1;
+        DPP_CHECK(apply_spec(ctx, op, K->t, K->r, true, nullptr, &nb));
+      }
     }
     DPP_CUDA(cudaEventRecord(e1, ctx->stream));
     DPP_CUDA(cudaEventSynchronize(e1));

@@ -47,7 +47,7 @@ int cg_xr_update(dpp_context* ctx, const VecLayout& L, double* x, double* r, con
                  const double* dinv, bool fused_pc, int slot, PostOp post);
 
 // fused CG iteration on uniform grids (cg_fused_uniform.cu): padded private layout + TMA loads
-bool cg_fused_available(const dpp_context* ctx, int nf, int operator_mode, int pc_type);
+bool cg_fused_available(dpp_context* ctx, int nf, int operator_mode, int pc_type);
 // (the reductions + PETSc bookkeeping after each kernel are folded into the kernels, or run as
 //  reduce_partials + NCCL when neither single-GPU nor peer-memory)
 int cg_fused_variant(dpp_context* ctx);   // 1: deferred x update (direction ring), 0: x updated in the apply kernel

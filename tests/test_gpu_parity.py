@@ -710,6 +710,45 @@ def test_q2_cg_jacobi_iteration_parity(cells):
     assert rel_err(u, ref.u) < 1e-9
 
 
+@pytest.mark.parametrize("cells", [(20, 17, 33), (6, 7, 5), (2, 1, 1), (1, 1, 1), (40, 9), (7, 70), (9, 24, 40)])
+@pytest.mark.parametrize("preset", ["jacobi", "none"])
+def test_q2_fused_cg_equals_unfused_sequence(cells, preset, monkeypatch):
+    """Degree 2 on a uniform grid: the two-kernel iteration (k_cg_fused_apply_q2 + r-update with the direction ring)
+    against the unfused apply / xr-update / p-update sequence -- same iteration count, same history to rounding, same
+    solution; ragged tile sizes, 2-D meshes, the full-boundary Dirichlet set (class mask) and a partial one (row
+    fix-up kernel), repeated solves on one handle, and the one-field blocks of the Picard solve."""
+    W, p, bcs, _ = make_problem(cells, 2)
+    params = {**(pb.B200_CG_JACOBI_PARAMS if preset == "jacobi" else pb.B200_CG_PARAMS), "b200_history": 8192}
+    for use_bcs in (bcs, [bcs[0]]):
+        monkeypatch.delenv("DPP_NO_FUSED_Q2", raising=False)
+        s1, u1, i1 = _solve_vec(W, p, use_bcs, params)
+        assert pb.handle_for(W).fused_cg_supported()
+        s1b, u1b, _ = _solve_vec(W, p, use_bcs, params)
+        monkeypatch.setenv("DPP_NO_FUSED_Q2", "1")
+        s2, u2, i2 = _solve_vec(W, p, use_bcs, params)
+        monkeypatch.delenv("DPP_NO_FUSED_Q2", raising=False)
+        assert np.array_equal(u1, u1b) and s1.iteration_number == s1b.iteration_number
+        if preset == "jacobi":
+            assert s1.iteration_number == s2.iteration_number
+            assert np.allclose(i1.history, i2.history, rtol=1e-8, atol=0)
+        else:
+            assert its_close(s1.iteration_number, s2.iteration_number)
+        assert i1.converged_reason == i2.converged_reason
+        # both stop at rtol 1e-7 of their own (rounding-different) residual recurrences; unpreconditioned CG on the
+        # badly scaled system leaves a larger part of that in the solution
+        assert rel_err(u1, u2) < (1e-8 if preset == "jacobi" else 1e-6)
+    if preset == "jacobi":
+        n1 = pb.solve_dpp_nonlinear(W, p, bcs, solver_parameters=pb.B200_PICARD_SPLIT_PARAMS)
+        v1 = np.concatenate([n1.solution.sub(0).dat.data, n1.solution.sub(1).dat.data])
+        monkeypatch.setenv("DPP_NO_FUSED_Q2", "1")
+        n2 = pb.solve_dpp_nonlinear(W, p, bcs, solver_parameters=pb.B200_PICARD_SPLIT_PARAMS)
+        v2 = np.concatenate([n2.solution.sub(0).dat.data, n2.solution.sub(1).dat.data])
+        monkeypatch.delenv("DPP_NO_FUSED_Q2", raising=False)
+        assert its_close(n1.iteration_number, n2.iteration_number)
+        assert rel_err(v1, v2) < 1e-7
+    pb.release_handles()
+
+
 def test_q2_block_picard_config4_shape():
     """BASELINE configs[3] at a size the oracle reaches: Q2 hexes, scale-splitting Picard, 6 outer iterations."""
     W, p, bcs, osys = make_problem((6, 6, 6), 2)
