@@ -805,8 +805,10 @@ struct __align__(16) SmemQ2 {
   int last_flag;
 };
 
-template <int NF>
-__global__ void __launch_bounds__(Q2NT, 3) k_cg_fused_apply_q2(const Q2FArgs s) {
+// OCC = resident CTAs per SM the register budget is cut for: 3 for two fields (168 registers), 4 for the one-field
+// blocks of the Picard / fieldsplit solves (122 registers; measured at 128^3: 4 -> 1466 ms, 3 -> 1525 ms, 5 -> 1490 ms)
+template <int NF, int OCC>
+__global__ void __launch_bounds__(Q2NT, OCC) k_cg_fused_apply_q2(const Q2FArgs s) {
   extern __shared__ __align__(16) unsigned char smem_raw_q2[];
   SmemQ2<NF>& sm = *reinterpret_cast<SmemQ2<NF>*>(smem_raw_q2);
   const int tid = threadIdx.x;
@@ -1393,18 +1395,18 @@ static int launch_apply_q2(dpp_context* ctx, FusedState* F, int nf, const Coef& 
     ctx->set_error("fused CG (degree 2): plane too wide for the partials scratch");
     return DPP_ERR_INVALID;
   }
-  s.nseg = choose_x_segments(tiles, nown, ctx->sm_count * 3, kMaxPartialBlocks, 2 * Q2H);
+  s.nseg = choose_x_segments(tiles, nown, ctx->sm_count * (nf == 1 ? 4 : 3), kMaxPartialBlocks, 2 * Q2H);
   if (const char* e = getenv("DPP_FUSED_SCHED"))
     if (atoi(e) > 0 && (long long)tiles * atoi(e) <= kMaxPartialBlocks) s.nseg = std::min(atoi(e), nown);
   static bool attr = false;
   if (!attr) {
-    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<2>)));
-    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<1>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<2>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<1>)));
     attr = true;
   }
   const dim3 grid(tiles * s.nseg), block(Q2NT);
-  if (nf == 2) DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<2>, grid, block, sizeof(SmemQ2<2>), ctx->stream, s));
-  else DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<1>, grid, block, sizeof(SmemQ2<1>), ctx->stream, s));
+  if (nf == 2) DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<2, 3>, grid, block, sizeof(SmemQ2<2>), ctx->stream, s));
+  else DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<1, 4>, grid, block, sizeof(SmemQ2<1>), ctx->stream, s));
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   *n_partial_blocks = (int)grid.x;

@@ -1,4 +1,5 @@
-"""Profile driver: structured Q2 apply at 96^3 (time_apply launches)."""
+"""Profile driver: structured Q2 kernels at N^3 cells (default 96): the stand-alone apply (time_apply), the two kernels
+of the fused Jacobi-CG iteration (time_cg_kernels) and, with `solve`, 48 iterations of a real solve (ncu target)."""
 import sys
 sys.path.insert(0, '.')
 import perphil_b200 as pb
@@ -11,3 +12,12 @@ bcs = [pb.DirichletBC(W.sub(0), pb.Constant(1.0), "on_boundary"), pb.DirichletBC
 h = configured_handle(W, prm, bcs)
 ms = h.time_apply(reps=5, warmup=2, with_dot=True)
 print(f"Q2 {N}^3 apply {ms:.4f} ms  {2*h.n_nodes/ms/1e6:.1f} GDoF/s")
+if h.fused_cg_supported():
+    fa, fu, mv = h.time_cg_kernels(reps=10, warmup=3)
+    nb = 2 * h.n_nodes * 8
+    print(f"Q2 {N}^3 fused apply {fa:.4f} ms ({4*nb/fa/1e6:.0f} GB/s of 4 passes), r-update {fu:.4f} ms "
+          f"({3*nb/fu/1e6:.0f} GB/s of 3 passes), plain apply {mv:.4f} ms")
+if "solve" in sys.argv:
+    opt = h.default_options(); opt.max_it = 48
+    _, info = h.solve(opt, want_solution=False)
+    print(f"48 iterations: {info.solve_ms:.2f} ms  ({info.solve_ms/48:.4f} ms / iteration)")
