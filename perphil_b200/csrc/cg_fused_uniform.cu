@@ -430,6 +430,7 @@ struct RArgs {
   double* x;
   const double* pr[kXRing];  // direction ring (padded, field-blocked)
   const double* xring;       // [kXRing] alpha, [kXRing] iteration tag
+  long long up_win;          // doubles at the end of the owned range the upper neighbour mirrors (degree planes)
 };
 
 constexpr int UNROLL = 4;   // pairs of nodes per thread and loop trip: 2 arrays x 4 x 16 B = 128 B in flight per thread
@@ -437,16 +438,16 @@ constexpr int UNROLL = 4;   // pairs of nodes per thread and loop trip: 2 arrays
 __device__ __forceinline__ void push_halo(const RArgs& a, int f, long long q, double v) {
   if (a.halo.peer_r[0] != nullptr && q < a.ob + a.plane)
     a.halo.peer_r[0][f * a.halo.peer_field[0] + a.halo.peer_ghost_off[0] + (q - a.ob)] = v;
-  if (a.halo.peer_r[1] != nullptr && q >= a.oe - a.plane)
-    a.halo.peer_r[1][f * a.halo.peer_field[1] + a.halo.peer_ghost_off[1] + (q - (a.oe - a.plane))] = v;
+  if (a.halo.peer_r[1] != nullptr && q >= a.oe - a.up_win)
+    a.halo.peer_r[1][f * a.halo.peer_field[1] + a.halo.peer_ghost_off[1] + (q - (a.oe - a.up_win))] = v;
 }
 // the same for an aligned pair (q even; a pair never straddles a plane: planes hold an even number of doubles)
 __device__ __forceinline__ void push_halo2(const RArgs& a, int f, long long q, double2 v) {
   if (a.halo.peer_r[0] != nullptr && q < a.ob + a.plane)
     *reinterpret_cast<double2*>(a.halo.peer_r[0] + f * a.halo.peer_field[0] + a.halo.peer_ghost_off[0] + (q - a.ob)) = v;
-  if (a.halo.peer_r[1] != nullptr && q >= a.oe - a.plane)
+  if (a.halo.peer_r[1] != nullptr && q >= a.oe - a.up_win)
     *reinterpret_cast<double2*>(a.halo.peer_r[1] + f * a.halo.peer_field[1] + a.halo.peer_ghost_off[1] +
-                                (q - (a.oe - a.plane))) = v;
+                                (q - (a.oe - a.up_win))) = v;
 }
 
 __device__ __forceinline__ int node_class(const RArgs& a, unsigned q) {
@@ -606,9 +607,11 @@ __global__ void __launch_bounds__(VT, 3) k_cg_r_update(const RArgs a) {
 __global__ void __launch_bounds__(VT) k_push_planes(const RArgs a) {
   const int f = blockIdx.y;
   const double* rf = a.r + (long long)f * a.field;
-  for (long long t = (long long)blockIdx.x * VT + threadIdx.x; t < a.plane; t += (long long)gridDim.x * VT) {
-    push_halo(a, f, a.ob + t, rf[a.ob + t]);
-    if (a.oe - a.plane != a.ob) push_halo(a, f, a.oe - a.plane + t, rf[a.oe - a.plane + t]);
+  // first owned plane (lower neighbour) and the last up_win doubles (upper neighbour); a range may be both
+  for (long long t = (long long)blockIdx.x * VT + threadIdx.x; t < a.plane + a.up_win; t += (long long)gridDim.x * VT) {
+    const long long q = t < a.plane ? a.ob + t : a.oe - a.up_win + (t - a.plane);
+    if (t >= a.plane && q < a.ob + a.plane) continue;   // already pushed (to both sides) by the first part
+    push_halo(a, f, q, rf[q]);
   }
 }
 
@@ -1133,10 +1136,11 @@ void cg_fused_destroy(dpp_context* ctx) {
 static int fused_state(dpp_context* ctx, FusedState** out);
 static int ring_state(dpp_context* ctx, FusedState* F);
 
-// degree 2: single-GPU handles only (the slab halo of the padded residual is two planes wide on the lower side and
-// still goes through the unfused sequence), and only with the direction ring (the kernel has no in-kernel x update)
+// degree 2: single GPU, or slabs whose residual halo goes through peer memory (the r-update kernel stores its boundary
+// planes into the neighbours: one plane down, two up; without peer memory the unfused sequence with its NCCL halos
+// runs), and only with the direction ring (the kernel has no in-kernel x update)
 static bool q2_fused_usable(dpp_context* ctx) {
-  if (ctx->world != 1 || getenv("DPP_NO_FUSED_Q2") != nullptr) return false;
+  if (!(ctx->world == 1 || comm_ipc_halo_ready(ctx)) || getenv("DPP_NO_FUSED_Q2") != nullptr) return false;
   FusedState* F = nullptr;
   if (fused_state(ctx, &F) != DPP_OK) { ctx->err.clear(); cudaGetLastError(); return false; }
   return ring_state(ctx, F) == DPP_OK;
@@ -1456,6 +1460,7 @@ static int make_rargs(dpp_context* ctx, FusedState* F, int nf, int slot, const d
   a.dom_hi = ctx->dom_hi;
   a.q2 = ctx->grid.band == 2 ? 1 : 0;
   a.plane = F->plane;
+  a.up_win = (long long)ctx->grid.band * F->plane;
   a.halo = comm_ipc_halo(ctx);
   if (fld != nullptr) {
     for (int f = 0; f < nf; ++f) {
@@ -1646,8 +1651,9 @@ int cg_fused_x_finalize(dpp_context* ctx, int nf, long long its, int slot, doubl
 }
 
 double* cg_fused_r_buffer(dpp_context* ctx, long long* field, long long* plane) {
-  if (!(ctx->family == DPP_KERNEL_STRUCTURED && ctx->grid.band == 1 && ctx->grid_uniform && encode_fn() != nullptr))
-    return nullptr;
+  const bool q1 = ctx->grid.band == 1 && ctx->grid_uniform && encode_fn() != nullptr;
+  const bool q2 = ctx->grid.band == 2 && ctx->q2_uniform;
+  if (!(ctx->family == DPP_KERNEL_STRUCTURED && (q1 || q2))) return nullptr;
   FusedState* F = nullptr;
   if (fused_state(ctx, &F) != DPP_OK) return nullptr;
   *field = F->field;
@@ -1668,7 +1674,7 @@ int cg_fused_halo_r(dpp_context* ctx, int nf, bool after_update, int slot) {
     DPP_CHECK(reduce_partials(ctx, 0, 1, slot, POST_NONE, 30));
     RArgs a{};
     DPP_CHECK(make_rargs(ctx, F, nf, slot, ctx->d_dtab, &a));
-    dim3 grid((unsigned)std::min<long long>((F->plane + VT - 1) / VT, (long long)ctx->sm_count * 4), nf);
+    dim3 grid((unsigned)std::min<long long>((F->plane + a.up_win + VT - 1) / VT, (long long)ctx->sm_count * 4), nf);
     k_push_planes<<<grid, VT, 0, ctx->stream>>>(a);
     ctx->launches++;
     DPP_CUDA(cudaGetLastError());

@@ -501,7 +501,7 @@ int dpp_comm_ipc_export(dpp_handle ctx, void* blob_out) {
       }
     }
     long long field = 0, plane = 0;
-    double* r = dpp::cg_fused_r_buffer(ctx, &field, &plane);   // only the fused (uniform Q1) path has one
+    double* r = dpp::cg_fused_r_buffer(ctx, &field, &plane);   // only the fused (uniform-grid) CG paths have one
     if (r != nullptr && (b.valid & 1)) {
       const long long uplane = (long long)ctx->grid.n[1] * ctx->grid.n[2];
       if (cudaIpcGetMemHandle(&b.r_handle, r) == cudaSuccess) {
@@ -577,8 +577,9 @@ int dpp_comm_ipc_import(dpp_handle ctx, const void* blobs) {
     C->r_peer[s] = static_cast<double*>(m);
     C->r_peer_field[s] = B[peer].field;
     // my first owned plane is the lower neighbour's upper ghost (its local plane i_end);
-    // my last owned plane is the upper neighbour's lower ghost (its local plane i_begin - 1)
-    C->r_peer_ghost_off[s] = (s == 0 ? (long long)B[peer].i_end : (long long)B[peer].i_begin - 1) * B[peer].plane;
+    // my last `degree` owned planes are the upper neighbour's lower ghosts (its local planes i_begin - degree ..)
+    const int band = ctx->family == DPP_KERNEL_STRUCTURED ? std::max(1, ctx->grid.band) : 1;
+    C->r_peer_ghost_off[s] = (s == 0 ? (long long)B[peer].i_end : (long long)B[peer].i_begin - band) * B[peer].plane;
     if (C->r_peer_ghost_off[s] < 0) return DPP_OK;
   }
   C->ipc_halo = all_r;

@@ -36,20 +36,23 @@ def _spawn(nproc, args, env_extra=None, timeout=600):
     return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
 
 
-@pytest.mark.parametrize("size,degree,env", [(32, 1, {}), (32, 1, {"DPP_NO_IPC": "1"}), (12, 2, {}), (12, 2, {"DPP_NO_IPC": "1"})])
+@pytest.mark.parametrize("size,degree,env", [(32, 1, {}), (32, 1, {"DPP_NO_IPC": "1"}), (12, 2, {}), (20, 2, {}),
+                                             (12, 2, {"DPP_NO_IPC": "1"})])
 def test_two_rank_slab_solves_equal_single_gpu(size, degree, env):
     if _gpus() < 2:
         pytest.skip("needs >= 2 visible GPUs")
     out = _spawn(2, [size, degree], env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MGPU OK" in out.stdout, out.stdout[-3000:]
-    # peer_memory bits: 1 mailbox all-reduce, 2 fused-CG halo push (Q1 uniform only), 4 halo inboxes for generic vectors
-    want_ipc = "ipc=0" if env else ("ipc=7" if degree == 1 else "ipc=5")
+    # peer_memory bits: 1 mailbox all-reduce, 2 fused-CG halo push (uniform grids, Q1 and Q2), 4 halo inboxes for
+    # generic vectors
+    want_ipc = "ipc=0" if env else "ipc=7"
     assert want_ipc in out.stdout, out.stdout[-2000:]
 
 
-def test_four_rank_slab_solves_equal_single_gpu():
+@pytest.mark.parametrize("size,degree", [(48, 1), (16, 2)])
+def test_four_rank_slab_solves_equal_single_gpu(size, degree):
     if _gpus() < 4:
         pytest.skip("needs >= 4 visible GPUs")
-    out = _spawn(4, [48, 1])
+    out = _spawn(4, [size, degree])
     assert out.returncode == 0 and "MGPU OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
