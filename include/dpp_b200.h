@@ -250,6 +250,9 @@ int dpp_time_apply(dpp_handle h, int operator_mode, int warmup, int reps, int wi
  * matvec_ms = the same TMA kernel in plain mode (w = A p, fused <p,Ap>: PETSc MatMult on the path).
  * Returns DPP_ERR_INVALID when the handle does not run the fused path. */
 int dpp_time_cg_kernels(dpp_handle h, int warmup, int reps, double* apply_ms, double* update_ms, double* matvec_ms);
+/* the same two kernels on the one-field diagonal block of `field` (0 or 1): the iteration of the block solves inside
+ * PCFIELDSPLIT and the block Picard solver (solvers/solver.py:167-172 sub-KSPs, :198-262 solve_dpp_nonlinear). */
+int dpp_time_cg_block_kernels(dpp_handle h, int field, int warmup, int reps, double* apply_ms, double* update_ms);
 /* device milliseconds of the two assembly phases: symbolic (node graph, row pointers, scatter permutation,
  * block pattern; rebuilt from scratch) and numeric (mean of `reps` value fills through the permutation; the
  * bandwidth model is 12 B per stored entry: 8 B value written + 4 B column index of the pattern). */

@@ -85,6 +85,8 @@ _PROTOTYPES = {
     "dpp_time_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "dpp_time_cg_kernels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double)]),
+    "dpp_time_cg_block_kernels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double)]),
     "dpp_kernel_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "dpp_plan_x_segments": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dpp_nccl_unique_id": (C.c_int, [C.c_void_p]),

@@ -271,6 +271,13 @@ class DppHandle:
                     "dpp_time_cg_kernels")
         return a.value, u.value, m.value
 
+    def time_cg_block_kernels(self, field: int = 0, reps: int = 20, warmup: int = 3):
+        """(apply_ms, update_ms) of the fused Jacobi-CG iteration on the one-field diagonal block of `field`."""
+        a, u = C.c_double(), C.c_double()
+        self._check(self._lib.dpp_time_cg_block_kernels(self._h, int(field), warmup, reps, C.byref(a), C.byref(u)),
+                    "dpp_time_cg_block_kernels")
+        return a.value, u.value
+
     def error_norms(self, u: Optional[np.ndarray] = None, exact: Optional[np.ndarray] = None, nq: int = 6):
         """(L2_1, L2_2, H1semi_1, H1semi_2) of u - exact; u None = the last solve's solution, exact None = the
         manufactured closed form for the handle's parameters."""

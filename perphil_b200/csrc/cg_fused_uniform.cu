@@ -762,8 +762,8 @@ __global__ void k_dinv_table(GridDesc g, Coef c, int nf, int jacobi, int zc0, in
 // Passes per iteration: r, p_old in; p, w out (4) + r-update 3 + x 17/15 = 8.13, against 13 + reciprocal diagonal
 // for the unfused sequence this replaces.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int Q2K = 32, Q2J = 8, Q2H = 2, Q2ROW = Q2K + 2 * Q2H, Q2SLOT = (Q2J + 2 * Q2H) * Q2ROW, Q2RING = 3;
-constexpr int Q2PT = 16, Q2NT = Q2PT * Q2J;     // 16 pair-threads per row, 128 threads
+constexpr int Q2K = 32, Q2H = 2, Q2ROW = Q2K + 2 * Q2H, Q2RING = 3;
+constexpr int Q2PT = 16;     // 16 pair-threads per row; TJ rows per tile -> 16 * TJ threads, (TJ + 4) x 36 halo'd tile
 
 struct AxisQ2 {     // assembled 1-D rows on an equally spaced axis; [0] interior, [1] domain-boundary centre
   double mV2, mV1, mVc[2], mM1, mMc;
@@ -796,12 +796,13 @@ __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr,
       : "memory");
 }
 
-template <int NF>
+template <int NF, int TJ>
 struct __align__(16) SmemQ2 {
-  double r[Q2RING][NF][Q2SLOT];
-  double p[Q2RING][NF][Q2SLOT];
+  static constexpr int SLOT = (TJ + 2 * Q2H) * Q2ROW;
+  double r[Q2RING][NF][SLOT];
+  double p[Q2RING][NF][SLOT];
   double dtab[2 * kClsPerField];
-  double red[Q2NT / 32];
+  double red[Q2PT * TJ / 32];
   double fin[kFinishSmem];
   double spre[kPreScalars];
   unsigned long long seq_pre;
@@ -810,10 +811,11 @@ struct __align__(16) SmemQ2 {
 
 // OCC = resident CTAs per SM the register budget is cut for: 3 for two fields (168 registers), 4 for the one-field
 // blocks of the Picard / fieldsplit solves (122 registers; measured at 128^3: 4 -> 1466 ms, 3 -> 1525 ms, 5 -> 1490 ms)
-template <int NF, int OCC>
-__global__ void __launch_bounds__(Q2NT, OCC) k_cg_fused_apply_q2(const Q2FArgs s) {
+template <int NF, int OCC, int TJ>
+__global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FArgs s) {
+  constexpr int Q2J = TJ, Q2NT = Q2PT * TJ, Q2SLOT = SmemQ2<NF, TJ>::SLOT;
   extern __shared__ __align__(16) unsigned char smem_raw_q2[];
-  SmemQ2<NF>& sm = *reinterpret_cast<SmemQ2<NF>*>(smem_raw_q2);
+  SmemQ2<NF, TJ>& sm = *reinterpret_cast<SmemQ2<NF, TJ>*>(smem_raw_q2);
   const int tid = threadIdx.x;
   pdl_launch_dependents();
   if (tid < 2 * kClsPerField) sm.dtab[tid] = tid < kClsPerField * NF ? s.dtab[tid] : 1.0;   // per-solve constant
@@ -834,7 +836,7 @@ __global__ void __launch_bounds__(Q2NT, OCC) k_cg_fused_apply_q2(const Q2FArgs s
   const int i_lo = s.i_begin + bstart(seg, nown, s.nseg);
   const int i_hi = s.i_begin + bstart(seg + 1, nown, s.nseg);
   const int warp = tid >> 5, lane = tid & 31;
-  const int jr = warp + 4 * (lane >> 4);               // rows {w, w + 4} of a warp have one parity
+  const int jr = warp + (TJ / 2) * (lane >> 4);        // rows {w, w + TJ / 2} of a warp have one parity
   const int kp = 2 * (lane & 15);
   const int j = j0 + jr, k = k0 + kp;
   const bool rowV = (jr & 1) == 0;
@@ -1390,8 +1392,13 @@ static int launch_apply_q2(dpp_context* ctx, FusedState* F, int nf, const Coef& 
   s.dom_lo = ctx->dom_lo; s.dom_hi = ctx->dom_hi;
   s.fold = fold_args(ctx, slot, POST_CG_PAP, 0);
   s.fold.xring = F->d_xring;
+  // 8-row tiles, 128 threads; 3 CTAs per SM for two fields (168 registers), 4 for one.  16-row tiles (256 threads,
+  // halo'd tile 1.41x instead of 1.69x the output tile) measured the same within noise (config 4 at 128^3: 1516 / 1573
+  // against 1523 / 1495 ms): the stencil phase, not the combine, carries the kernel.
+  constexpr int TJ1 = 8, OCC1 = 4;
+  const int tj = nf == 2 ? 8 : TJ1;
   s.ntk = (g.n[2] + Q2K - 1) / Q2K;
-  s.ntj = (g.n[1] + Q2J - 1) / Q2J;
+  s.ntj = (g.n[1] + tj - 1) / tj;
   const int tiles = s.ntk * s.ntj;
   const int nown = s.i_end - s.i_begin;
   if (nown <= 0) { *n_partial_blocks = 0; return DPP_OK; }
@@ -1399,18 +1406,18 @@ static int launch_apply_q2(dpp_context* ctx, FusedState* F, int nf, const Coef& 
     ctx->set_error("fused CG (degree 2): plane too wide for the partials scratch");
     return DPP_ERR_INVALID;
   }
-  s.nseg = choose_x_segments(tiles, nown, ctx->sm_count * (nf == 1 ? 4 : 3), kMaxPartialBlocks, 2 * Q2H);
+  s.nseg = choose_x_segments(tiles, nown, ctx->sm_count * (nf == 1 ? OCC1 : 3), kMaxPartialBlocks, 2 * Q2H);
   if (const char* e = getenv("DPP_FUSED_SCHED"))
     if (atoi(e) > 0 && (long long)tiles * atoi(e) <= kMaxPartialBlocks) s.nseg = std::min(atoi(e), nown);
   static bool attr = false;
   if (!attr) {
-    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<2>)));
-    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<1>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<2, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<2, 8>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<1, OCC1, TJ1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<1, TJ1>)));
     attr = true;
   }
-  const dim3 grid(tiles * s.nseg), block(Q2NT);
-  if (nf == 2) DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<2, 3>, grid, block, sizeof(SmemQ2<2>), ctx->stream, s));
-  else DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<1, 4>, grid, block, sizeof(SmemQ2<1>), ctx->stream, s));
+  const dim3 grid(tiles * s.nseg), block(Q2PT * tj);
+  if (nf == 2) DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<2, 3, 8>, grid, block, sizeof(SmemQ2<2, 8>), ctx->stream, s));
+  else DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<1, OCC1, TJ1>, grid, block, sizeof(SmemQ2<1, TJ1>), ctx->stream, s));
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   *n_partial_blocks = (int)grid.x;

@@ -509,6 +509,13 @@ int dpp_time_cg_kernels(dpp_handle ctx, int warmup, int reps, double* apply_ms, 
   return dpp::krylov_time_cg_kernels(ctx, warmup, reps, apply_ms, update_ms, matvec_ms);
 }
 
+int dpp_time_cg_block_kernels(dpp_handle ctx, int field, int warmup, int reps, double* apply_ms, double* update_ms) {
+  if (!ctx || reps <= 0 || warmup < 0 || !apply_ms || !update_ms || field < 0 || field > 1) return DPP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  double unused = 0.0;
+  return dpp::krylov_time_cg_kernels(ctx, warmup, reps, apply_ms, update_ms, &unused, 1, field);
+}
+
 int dpp_error_norms(dpp_handle ctx, const double* u_host, const double* exact_host, int nq, double* out4) {
   if (!ctx || !out4) return DPP_ERR_INVALID;
   cudaSetDevice(ctx->device);

@@ -289,7 +289,7 @@ int krylov_solve(dpp_context* ctx, const dpp_options* opt, double* u_host, dpp_r
                  double* hist_host, int32_t hist_cap);
 void krylov_destroy(dpp_context* ctx);
 int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply_ms, double* update_ms,
-                           double* matvec_ms);
+                           double* matvec_ms, int nf = 2, int field = 0);
 
 template <typename T>
 inline int dev_alloc(dpp_context* ctx, T** p, int64_t count) {

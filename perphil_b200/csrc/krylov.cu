@@ -942,12 +942,12 @@ int krylov_lanczos(dpp_context* ctx, int which, int steps, unsigned long long se
 }
 
 int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply_ms, double* update_ms,
-                           double* matvec_ms) {
+                           double* matvec_ms, int nf, int field) {
   if (!ctx->have_params) {
     ctx->set_error("dpp_time_cg_kernels: call dpp_set_params first");
     return DPP_ERR_STATE;
   }
-  if (!cg_fused_available(ctx, 2, DPP_OP_MATRIX_FREE, DPP_PC_JACOBI)) {
+  if (!cg_fused_available(ctx, nf, DPP_OP_MATRIX_FREE, DPP_PC_JACOBI)) {
     ctx->set_error("dpp_time_cg_kernels: the handle does not run the fused uniform-grid CG path");
     return DPP_ERR_INVALID;
   }
@@ -970,21 +970,22 @@ int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply
   hs[S_RNORM0] = 1e300; hs[S_TTOL] = 0.0;  // the folded convergence test never fires while timing
   DPP_CUDA(cudaMemcpyAsync(S, hs, sizeof(double) * S_SLOT_SIZE, cudaMemcpyHostToDevice, ctx->stream));
   DPP_CUDA(cudaStreamSynchronize(ctx->stream));
-  const Coef coef = dpp_coef(ctx);
+  // nf = 2: the monolithic operator; nf = 1: the diagonal block of `field` (Picard / fieldsplit block solves)
+  const Coef coef = nf == 2 ? dpp_coef(ctx) : block_coef(ctx, field, field);
   double* dtab = ctx->d_dtab;
-  const int fld[2] = {0, 1};
-  DPP_CHECK(cg_fused_table(ctx, coef, 2, DPP_PC_JACOBI, fld, dtab));
+  const int fld[2] = {nf == 2 ? 0 : field, 1};
+  DPP_CHECK(cg_fused_table(ctx, coef, nf, DPP_PC_JACOBI, fld, dtab));
   cudaEvent_t e0, e1;
   DPP_CUDA(cudaEventCreate(&e0));
   DPP_CUDA(cudaEventCreate(&e1));
   float ms = 0;
   int nb = 0;
   double* outs[3] = {apply_ms, update_ms, matvec_ms};
-  for (int pass = 0; pass < 3; ++pass) {
+  for (int pass = 0; pass < (nf == 2 ? 3 : 2); ++pass) {
     for (int i = -warmup; i < reps; ++i) {
       if (i == 0) DPP_CUDA(cudaEventRecord(e0, ctx->stream));
-      if (pass == 0) DPP_CHECK(cg_fused_apply(ctx, 2, coef, i + warmup, fld, slot, dtab));
-      else if (pass == 1) DPP_CHECK(cg_fused_r_update(ctx, 2, fld, slot, dtab));
+      if (pass == 0) DPP_CHECK(cg_fused_apply(ctx, nf, coef, i + warmup, fld, slot, dtab));
+      else if (pass == 1) DPP_CHECK(cg_fused_r_update(ctx, nf, fld, slot, dtab));
       else if (ctx->grid.band == 1) DPP_CHECK(cg_fused_plain_apply(ctx, 2, coef, true, &nb));
       else {   // degree 2: the stand-alone stencil kernel on the C-ABI layout (apply_structured_q2.cu)
         OpSpec op{};

@@ -645,6 +645,17 @@ def test_fused_cg_kernel_timer_runs():
     # the timer scribbles on the work vectors only: a solve afterwards is unaffected
     sol = pb.solve_dpp(W, p, bcs, solver_parameters=pb.B200_CG_JACOBI_PARAMS)
     assert sol.iteration_number == 31
+    ab, ub = h.time_cg_block_kernels(1, reps=3, warmup=1)
+    assert ab > 0 and ub > 0
+    assert pb.solve_dpp(W, p, bcs, solver_parameters=pb.B200_CG_JACOBI_PARAMS).iteration_number == 31
+    # degree 2: the cp.async kernel of the same iteration
+    W2, p2, bcs2, _ = make_problem((6, 7, 5), 2)
+    h2 = configured_handle(W2, p2, bcs2)
+    ref = pb.solve_dpp(W2, p2, bcs2, solver_parameters=pb.B200_CG_JACOBI_PARAMS).iteration_number
+    a2, u2, m2 = h2.time_cg_kernels(reps=3, warmup=1)
+    ab2, ub2 = h2.time_cg_block_kernels(0, reps=3, warmup=1)
+    assert min(a2, u2, m2, ab2, ub2) > 0
+    assert pb.solve_dpp(W2, p2, bcs2, solver_parameters=pb.B200_CG_JACOBI_PARAMS).iteration_number == ref
 
 
 # ---------------------------------------------------------------------------------------------
