@@ -235,17 +235,20 @@ __global__ void __launch_bounds__(NT, 2) k_apply_q2(const Q2Args s) {
 // Per node and field: ~36 fp64 operations in-plane + ~10 along x (table kernel: 65 + 15) and 0.75 shared-memory
 // wavefronts (1.56).  Same plane streaming (cp.async ring, zero-filled halo) and register queue along x.
 // ---------------------------------------------------------------------------------------------------------------
-struct AxisCoef {     // [0] interior, [1] domain-boundary centre entries of the vertex row
-  double mV2, mV1, mVc[2], mM1, mMc;
-  double kV2, kV1, kVc[2], kM1, kMc;
-};
-
+// The assembled 1-D rows on an equally spaced axis are (h/30) x {-1, 2, 8|4, 2, -1} / {2, 16, 2} (mass: vertex / mid
+// row; 4 = one cell only, on the domain boundary) and 1/(3h) x {1, -8, 14|7, -8, 1} / {-8, 16, -8} (stiffness).  The
+// kernel evaluates the INTEGER stencils -- immediate operands of the fp64 instructions: no constant loads, no uniform
+// registers (the 30 coefficients of the first version spilled them: 7 % of the issued instructions were UR moves) --
+// and the scale factors ride on three coefficients per field pair:
+//   y_f = sum_g a1[f][g] (Kx' c') + a2[f][g] (Mx' d') + a3[f][g] (Mx' c'),
+//   c' = (My' x Mz') x,  d' = rho_y (Ky' x Mz') x + rho_z (My' x Kz') x,  rho = (1/(3h)) / (h/30) = 10 / h^2.
 struct Q2UArgs {
   int n[3];
-  AxisCoef ax[3];
+  double rho_y, rho_z;
+  double a1[2][2], a2[2][2], a3[2][2];
+  double cxM, cxK;           // centre entries of the boundary vertex rows along x: 4, 7 (dummy axis of a 2-D mesh: 1, 0)
   const double* x[2];
   double* y[2];
-  Coef c;
   double* dot_partials;
   int i_begin, i_end;
   int ntj, ntk, nseg;
@@ -293,10 +296,8 @@ __global__ void __launch_bounds__(UNT, 3) k_apply_q2u(const Q2UArgs s) {
     coff[q] = cok[q] ? (long long)jj * nk + kk : 0;
   }
   // per-thread centre coefficients (boundary rows / columns have one cell instead of two)
-  const AxisCoef& ay = s.ax[1];
-  const AxisCoef& az = s.ax[2];
-  const int jb = (j == 0 || j == nj - 1) ? 1 : 0, kb = (k == 0 || k == nk - 1) ? 1 : 0;
-  const double myVc = ay.mVc[jb], kyVc = ay.kVc[jb], mzVc = az.mVc[kb], kzVc = az.kVc[kb];
+  const bool jb = (j == 0 || j == nj - 1), kb = (k == 0 || k == nk - 1);
+  const double myVc = jb ? 4.0 : 8.0, kyVc = jb ? 7.0 : 14.0, mzVc = kb ? 4.0 : 8.0, kzVc = kb ? 7.0 : 14.0;
 
   double qcV[NF][5], qdV[NF][5], qcM[NF][5], qdM[NF][5], cenV[NF][3], cenM[NF][3];
 #pragma unroll
@@ -329,15 +330,17 @@ __global__ void __launch_bounds__(UNT, 3) k_apply_q2u(const Q2UArgs s) {
     const double2 p0 = *reinterpret_cast<const double2*>(T);                                          \
     const double2 p1 = *reinterpret_cast<const double2*>((T) + 2);                                    \
     const double2 p2 = *reinterpret_cast<const double2*>((T) + 4);                                    \
-    const double s2 = p0.x + p2.x, s1 = p0.y + p1.y, sm = p1.x + p2.x;                                \
-    const double tzV = fma(az.mV2, s2, fma(az.mV1, s1, mzVc * p1.x));                                 \
-    const double uzV = fma(az.kV2, s2, fma(az.kV1, s1, kzVc * p1.x));                                 \
-    const double tzM = fma(az.mM1, sm, az.mMc * p1.y);                                                \
-    const double uzM = fma(az.kM1, sm, az.kMc * p1.y);                                                \
+    const double s2 = p0.x + p2.x, s1 = p0.y + p1.y, sm = p1.x + p2.x, e16 = 16.0 * p1.y;             \
+    const double tzV = fma(2.0, s1, fma(mzVc, p1.x, -s2));                                            \
+    const double uzV = fma(-8.0, s1, fma(kzVc, p1.x, s2));                                            \
+    const double tzM = fma(2.0, sm, e16);                                                             \
+    const double uzM = fma(-8.0, sm, e16);                                                            \
     cV = fma(MYR, tzV, cV);                                                                           \
-    dV = fma(KYR, tzV, fma(MYR, uzV, dV));                                                            \
+    d1V = fma(KYR, tzV, d1V);                                                                         \
+    d2V = fma(MYR, uzV, d2V);                                                                         \
     cM = fma(MYR, tzM, cM);                                                                           \
-    dM = fma(KYR, tzM, fma(MYR, uzM, dM));                                                            \
+    d1M = fma(KYR, tzM, d1M);                                                                         \
+    d2M = fma(MYR, uzM, d2M);                                                                         \
   }
 
   issue(i_first, 0);
@@ -364,18 +367,21 @@ __global__ void __launch_bounds__(UNT, 3) k_apply_q2u(const Q2UArgs s) {
     for (int f = 0; f < NF; ++f) {
       double cV = 0.0, dV = 0.0, cM = 0.0, dM = 0.0, xcV = 0.0, xcM = 0.0;
       if (in && actV) {
+        double d1V = 0.0, d2V = 0.0, d1M = 0.0, d2M = 0.0;
         const double* t = &xs[slot][f][jr * SROW + kp];
         if (rowV) {
-          DPP_Q2U_ROW(t, ay.mV2, ay.kV2)
-          DPP_Q2U_ROW(t + SROW, ay.mV1, ay.kV1)
+          DPP_Q2U_ROW(t, -1.0, 1.0)
+          DPP_Q2U_ROW(t + SROW, 2.0, -8.0)
           DPP_Q2U_ROW(t + 2 * SROW, myVc, kyVc)
-          DPP_Q2U_ROW(t + 3 * SROW, ay.mV1, ay.kV1)
-          DPP_Q2U_ROW(t + 4 * SROW, ay.mV2, ay.kV2)
+          DPP_Q2U_ROW(t + 3 * SROW, 2.0, -8.0)
+          DPP_Q2U_ROW(t + 4 * SROW, -1.0, 1.0)
         } else {
-          DPP_Q2U_ROW(t + SROW, ay.mM1, ay.kM1)
-          DPP_Q2U_ROW(t + 2 * SROW, ay.mMc, ay.kMc)
-          DPP_Q2U_ROW(t + 3 * SROW, ay.mM1, ay.kM1)
+          DPP_Q2U_ROW(t + SROW, 2.0, -8.0)
+          DPP_Q2U_ROW(t + 2 * SROW, 16.0, 16.0)
+          DPP_Q2U_ROW(t + 3 * SROW, 2.0, -8.0)
         }
+        dV = fma(s.rho_y, d1V, s.rho_z * d2V);
+        dM = fma(s.rho_y, d1M, s.rho_z * d2M);
         xcV = t[2 * SROW + 2];
         xcM = t[2 * SROW + 3];
       }
@@ -390,31 +396,35 @@ __global__ void __launch_bounds__(UNT, 3) k_apply_q2u(const Q2UArgs s) {
     }
     const int io = ip - H;
     if (actV && io >= i_lo && io < i_hi) {
-      const AxisCoef& axx = s.ax[0];
-      double KxV[NF], MxV[NF], KxM[NF], MxM[NF];
+      // Kc = Kx' c', Md = Mx' d', Mc = Mx' c' (integer rows along x)
+      double KcV[NF], MdV[NF], McV[NF], KcM[NF], MdM[NF], McM[NF];
       if ((io & 1) == 0) {
-        const int xb = ((io == 0 && s.dom_lo) || (io == ni - 1 && s.dom_hi)) ? 1 : 0;
-        const double mc = axx.mVc[xb], kc = axx.kVc[xb];
+        const bool xb = (io == 0 && s.dom_lo) || (io == ni - 1 && s.dom_hi);
+        const double mc = xb ? s.cxM : 8.0, kc = xb ? s.cxK : 14.0;
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
           const double c2 = qcV[f][0] + qcV[f][4], c1 = qcV[f][1] + qcV[f][3], c0 = qcV[f][2];
           const double d2 = qdV[f][0] + qdV[f][4], d1 = qdV[f][1] + qdV[f][3], d0 = qdV[f][2];
-          MxV[f] = fma(axx.mV2, c2, fma(axx.mV1, c1, mc * c0));
-          KxV[f] = fma(axx.kV2, c2, fma(axx.kV1, c1, fma(kc, c0, fma(axx.mV2, d2, fma(axx.mV1, d1, mc * d0)))));
+          McV[f] = fma(2.0, c1, fma(mc, c0, -c2));
+          KcV[f] = fma(-8.0, c1, fma(kc, c0, c2));
+          MdV[f] = fma(2.0, d1, fma(mc, d0, -d2));
           const double e2 = qcM[f][0] + qcM[f][4], e1 = qcM[f][1] + qcM[f][3], e0 = qcM[f][2];
           const double g2 = qdM[f][0] + qdM[f][4], g1 = qdM[f][1] + qdM[f][3], g0 = qdM[f][2];
-          MxM[f] = fma(axx.mV2, e2, fma(axx.mV1, e1, mc * e0));
-          KxM[f] = fma(axx.kV2, e2, fma(axx.kV1, e1, fma(kc, e0, fma(axx.mV2, g2, fma(axx.mV1, g1, mc * g0)))));
+          McM[f] = fma(2.0, e1, fma(mc, e0, -e2));
+          KcM[f] = fma(-8.0, e1, fma(kc, e0, e2));
+          MdM[f] = fma(2.0, g1, fma(mc, g0, -g2));
         }
       } else {
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-          const double c1 = qcV[f][1] + qcV[f][3], c0 = qcV[f][2], d1 = qdV[f][1] + qdV[f][3], d0 = qdV[f][2];
-          MxV[f] = fma(axx.mM1, c1, axx.mMc * c0);
-          KxV[f] = fma(axx.kM1, c1, fma(axx.kMc, c0, fma(axx.mM1, d1, axx.mMc * d0)));
-          const double e1 = qcM[f][1] + qcM[f][3], e0 = qcM[f][2], g1 = qdM[f][1] + qdM[f][3], g0 = qdM[f][2];
-          MxM[f] = fma(axx.mM1, e1, axx.mMc * e0);
-          KxM[f] = fma(axx.kM1, e1, fma(axx.kMc, e0, fma(axx.mM1, g1, axx.mMc * g0)));
+          const double c1 = qcV[f][1] + qcV[f][3], c16 = 16.0 * qcV[f][2], d1 = qdV[f][1] + qdV[f][3];
+          McV[f] = fma(2.0, c1, c16);
+          KcV[f] = fma(-8.0, c1, c16);
+          MdV[f] = fma(2.0, d1, 16.0 * qdV[f][2]);
+          const double e1 = qcM[f][1] + qcM[f][3], e16 = 16.0 * qcM[f][2], g1 = qdM[f][1] + qdM[f][3];
+          McM[f] = fma(2.0, e1, e16);
+          KcM[f] = fma(-8.0, e1, e16);
+          MdM[f] = fma(2.0, g1, 16.0 * qdM[f][2]);
         }
       }
       const long long node = (long long)io * plane + own;
@@ -423,10 +433,8 @@ __global__ void __launch_bounds__(UNT, 3) k_apply_q2u(const Q2UArgs s) {
         double yV = 0.0, yM = 0.0;
 #pragma unroll
         for (int g = 0; g < NF; ++g) {
-          yV = fma(s.c.cK[f][g], KxV[g], yV);
-          yV = fma(s.c.cM[f][g], MxV[g], yV);
-          yM = fma(s.c.cK[f][g], KxM[g], yM);
-          yM = fma(s.c.cM[f][g], MxM[g], yM);
+          yV = fma(s.a1[f][g], KcV[g], fma(s.a2[f][g], MdV[g], fma(s.a3[f][g], McV[g], yV)));
+          yM = fma(s.a1[f][g], KcM[g], fma(s.a2[f][g], MdM[g], fma(s.a3[f][g], McM[g], yM)));
         }
         s.y[f][node] = yV;
         dot = fma(cenV[f][0], yV, dot);
@@ -453,20 +461,6 @@ __global__ void __launch_bounds__(UNT, 3) k_apply_q2u(const Q2UArgs s) {
       s.dot_partials[blockIdx.x] = t;
     }
   }
-}
-
-// vertex / mid rows of the assembled 1-D Q2 matrices on an equally spaced axis with cell size h
-AxisCoef axis_coef(int n_nodes, double h) {
-  AxisCoef a{};
-  if (n_nodes == 1) {   // dummy axis of a 2-D mesh: M = [1], K = [0]
-    a.mVc[0] = a.mVc[1] = 1.0;
-    a.mMc = 1.0;
-    return a;
-  }
-  const double b = h / 30.0, q = 1.0 / (3.0 * h);
-  a.mV2 = -b; a.mV1 = 2 * b; a.mVc[0] = 8 * b; a.mVc[1] = 4 * b; a.mM1 = 2 * b; a.mMc = 16 * b;
-  a.kV2 = q; a.kV1 = -8 * q; a.kVc[0] = 14 * q; a.kVc[1] = 7 * q; a.kM1 = -8 * q; a.kMc = 16 * q;
-  return a;
 }
 
 __global__ void k_premask_q2(long long n, const double* __restrict__ x, const uint8_t* __restrict__ m,
@@ -547,9 +541,24 @@ int structured_apply_q2(dpp_context* ctx, const OpArgs& a, int* n_partial_blocks
   }
   if (uniform) {
     Q2UArgs u{};
-    for (int d = 0; d < 3; ++d) { u.n[d] = g.n[d]; u.ax[d] = axis_coef(g.n[d], hh[d]); }
+    for (int d = 0; d < 3; ++d) u.n[d] = g.n[d];
+    {
+      // scale factors of the 1-D rows: mass h/30, stiffness 1/(3h); dummy axis of a 2-D mesh: M = [1], K = [0]
+      const bool dummy = g.n[0] == 1;
+      const double bmx = dummy ? 1.0 : hh[0] / 30.0, bkx = dummy ? 0.0 : 1.0 / (3.0 * hh[0]);
+      const double B = (hh[1] / 30.0) * (hh[2] / 30.0);
+      u.rho_y = 10.0 / (hh[1] * hh[1]);
+      u.rho_z = 10.0 / (hh[2] * hh[2]);
+      u.cxM = dummy ? 1.0 : 4.0;
+      u.cxK = dummy ? 0.0 : 7.0;
+      for (int f = 0; f < 2; ++f)
+        for (int q = 0; q < 2; ++q) {
+          u.a1[f][q] = a.c.cK[f][q] * bkx * B;
+          u.a2[f][q] = a.c.cK[f][q] * bmx * B;
+          u.a3[f][q] = a.c.cM[f][q] * bmx * B;
+        }
+    }
     for (int f = 0; f < a.nf; ++f) { u.x[f] = s.x[f]; u.y[f] = s.y[f]; }
-    u.c = a.c;
     u.dot_partials = a.dot_partials;
     u.i_begin = s.i_begin; u.i_end = s.i_end;
     u.ntj = s.ntj; u.ntk = s.ntk;

@@ -765,21 +765,21 @@ __global__ void k_dinv_table(GridDesc g, Coef c, int nf, int jacobi, int zc0, in
 constexpr int Q2K = 32, Q2H = 2, Q2ROW = Q2K + 2 * Q2H, Q2RING = 3;
 constexpr int Q2PT = 16;     // 16 pair-threads per row; TJ rows per tile -> 16 * TJ threads, (TJ + 4) x 36 halo'd tile
 
-struct AxisQ2 {     // assembled 1-D rows on an equally spaced axis; [0] interior, [1] domain-boundary centre
-  double mV2, mV1, mVc[2], mM1, mMc;
-  double kV2, kV1, kVc[2], kM1, kMc;
-};
-
 struct Q2FArgs {
   int n[3];
   int pitch;
   long long plane, field;
-  AxisQ2 ax[3];
+  // The assembled 1-D rows on an equally spaced axis are (h/30) x {-1, 2, 8|4, 2, -1} / {2, 16, 2} (mass, vertex / mid
+  // row; 4 on the domain boundary) and 1/(3h) x {1, -8, 14|7, -8, 1} / {-8, 16, -8} (stiffness): the kernel evaluates
+  // the integer stencils (immediate operands) and the scale factors ride on three coefficients per field pair:
+  // y_f = sum_g a1[f][g] (Kx' c') + a2[f][g] (Mx' d') + a3[f][g] (Mx' c'),  d' = rho_y (Ky' x Mz') p + rho_z (My' x Kz') p
+  double rho_y, rho_z;       // (1/(3h)) / (h/30) = 10 / h^2 of the y and z axes
+  double a1[2][2], a2[2][2], a3[2][2];
+  double cxM, cxK;           // centre entries of the boundary vertex rows along x: 4, 7 (dummy axis of a 2-D mesh: 1, 0)
   const double* r;
   const double* pin;
   double* pout;
   double* w;
-  Coef c;
   double* dot_partials;
   int i_begin, i_end;
   int ntj, ntk, nseg;
@@ -869,10 +869,8 @@ __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FA
   const unsigned sr_base = (unsigned)__cvta_generic_to_shared(&sm.r[0][0][0]);
   const unsigned sp_base = (unsigned)__cvta_generic_to_shared(&sm.p[0][0][0]);
 
-  const AxisQ2& ay = s.ax[1];
-  const AxisQ2& az = s.ax[2];
-  const int jb = (j == 0 || j == nj - 1) ? 1 : 0, kb = (k == 0 || k == nk - 1) ? 1 : 0;
-  const double myVc = ay.mVc[jb], kyVc = ay.kVc[jb], mzVc = az.mVc[kb], kzVc = az.kVc[kb];
+  const bool jb = (j == 0 || j == nj - 1), kb = (k == 0 || k == nk - 1);
+  const double myVc = jb ? 4.0 : 8.0, kyVc = jb ? 7.0 : 14.0, mzVc = kb ? 4.0 : 8.0, kzVc = kb ? 7.0 : 14.0;
 
   double qcV[NF][5], qdV[NF][5], qcM[NF][5], qdM[NF][5], cenV[NF][3], cenM[NF][3];
 #pragma unroll
@@ -907,15 +905,17 @@ __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FA
     const double2 p0 = *reinterpret_cast<const double2*>(T);                                          \
     const double2 p1 = *reinterpret_cast<const double2*>((T) + 2);                                    \
     const double2 p2 = *reinterpret_cast<const double2*>((T) + 4);                                    \
-    const double s2 = p0.x + p2.x, s1 = p0.y + p1.y, sm_ = p1.x + p2.x;                               \
-    const double tzV = fma(az.mV2, s2, fma(az.mV1, s1, mzVc * p1.x));                                 \
-    const double uzV = fma(az.kV2, s2, fma(az.kV1, s1, kzVc * p1.x));                                 \
-    const double tzM = fma(az.mM1, sm_, az.mMc * p1.y);                                               \
-    const double uzM = fma(az.kM1, sm_, az.kMc * p1.y);                                               \
+    const double s2 = p0.x + p2.x, s1 = p0.y + p1.y, sm_ = p1.x + p2.x, e16 = 16.0 * p1.y;            \
+    const double tzV = fma(2.0, s1, fma(mzVc, p1.x, -s2));                                            \
+    const double uzV = fma(-8.0, s1, fma(kzVc, p1.x, s2));                                            \
+    const double tzM = fma(2.0, sm_, e16);                                                            \
+    const double uzM = fma(-8.0, sm_, e16);                                                           \
     cV = fma(MYR, tzV, cV);                                                                           \
-    dV = fma(KYR, tzV, fma(MYR, uzV, dV));                                                            \
+    d1V = fma(KYR, tzV, d1V);                                                                         \
+    d2V = fma(MYR, uzV, d2V);                                                                         \
     cM = fma(MYR, tzM, cM);                                                                           \
-    dM = fma(KYR, tzM, fma(MYR, uzM, dM));                                                            \
+    d1M = fma(KYR, tzM, d1M);                                                                         \
+    d2M = fma(MYR, uzM, d2M);                                                                         \
   }
 
   __syncthreads();   // dtab, spre
@@ -955,18 +955,21 @@ __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FA
     for (int f = 0; f < NF; ++f) {
       double cV = 0.0, dV = 0.0, cM = 0.0, dM = 0.0, xcV = 0.0, xcM = 0.0;
       if (in && actV) {
+        double d1V = 0.0, d2V = 0.0, d1M = 0.0, d2M = 0.0;
         const double* t = &sm.p[slot][f][jr * Q2ROW + kp];
         if (rowV) {
-          DPP_Q2F_ROW(t, ay.mV2, ay.kV2)
-          DPP_Q2F_ROW(t + Q2ROW, ay.mV1, ay.kV1)
+          DPP_Q2F_ROW(t, -1.0, 1.0)
+          DPP_Q2F_ROW(t + Q2ROW, 2.0, -8.0)
           DPP_Q2F_ROW(t + 2 * Q2ROW, myVc, kyVc)
-          DPP_Q2F_ROW(t + 3 * Q2ROW, ay.mV1, ay.kV1)
-          DPP_Q2F_ROW(t + 4 * Q2ROW, ay.mV2, ay.kV2)
+          DPP_Q2F_ROW(t + 3 * Q2ROW, 2.0, -8.0)
+          DPP_Q2F_ROW(t + 4 * Q2ROW, -1.0, 1.0)
         } else {
-          DPP_Q2F_ROW(t + Q2ROW, ay.mM1, ay.kM1)
-          DPP_Q2F_ROW(t + 2 * Q2ROW, ay.mMc, ay.kMc)
-          DPP_Q2F_ROW(t + 3 * Q2ROW, ay.mM1, ay.kM1)
+          DPP_Q2F_ROW(t + Q2ROW, 2.0, -8.0)
+          DPP_Q2F_ROW(t + 2 * Q2ROW, 16.0, 16.0)
+          DPP_Q2F_ROW(t + 3 * Q2ROW, 2.0, -8.0)
         }
+        dV = fma(s.rho_y, d1V, s.rho_z * d2V);
+        dM = fma(s.rho_y, d1M, s.rho_z * d2M);
         xcV = t[2 * Q2ROW + 2];
         xcM = t[2 * Q2ROW + 3];
         if (pwr) {   // the direction of this iteration, for the next one and for the deferred x update
@@ -986,31 +989,35 @@ __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FA
     }
     const int io = ip - Q2H;
     if (actV && io >= i_lo && io < i_hi) {
-      const AxisQ2& axx = s.ax[0];
-      double KxV[NF], MxV[NF], KxM[NF], MxM[NF];
+      // Kc = Kx' c', Md = Mx' d', Mc = Mx' c' (integer rows along x)
+      double KcV[NF], MdV[NF], McV[NF], KcM[NF], MdM[NF], McM[NF];
       if ((io & 1) == 0) {
-        const int xb = ((io == 0 && s.dom_lo) || (io == ni - 1 && s.dom_hi)) ? 1 : 0;
-        const double mc = axx.mVc[xb], kc = axx.kVc[xb];
+        const bool xb = (io == 0 && s.dom_lo) || (io == ni - 1 && s.dom_hi);
+        const double mc = xb ? s.cxM : 8.0, kc = xb ? s.cxK : 14.0;
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
           const double c2 = qcV[f][0] + qcV[f][4], c1 = qcV[f][1] + qcV[f][3], c0 = qcV[f][2];
           const double d2 = qdV[f][0] + qdV[f][4], d1 = qdV[f][1] + qdV[f][3], d0 = qdV[f][2];
-          MxV[f] = fma(axx.mV2, c2, fma(axx.mV1, c1, mc * c0));
-          KxV[f] = fma(axx.kV2, c2, fma(axx.kV1, c1, fma(kc, c0, fma(axx.mV2, d2, fma(axx.mV1, d1, mc * d0)))));
+          McV[f] = fma(2.0, c1, fma(mc, c0, -c2));
+          KcV[f] = fma(-8.0, c1, fma(kc, c0, c2));
+          MdV[f] = fma(2.0, d1, fma(mc, d0, -d2));
           const double e2 = qcM[f][0] + qcM[f][4], e1 = qcM[f][1] + qcM[f][3], e0 = qcM[f][2];
           const double g2 = qdM[f][0] + qdM[f][4], g1 = qdM[f][1] + qdM[f][3], g0 = qdM[f][2];
-          MxM[f] = fma(axx.mV2, e2, fma(axx.mV1, e1, mc * e0));
-          KxM[f] = fma(axx.kV2, e2, fma(axx.kV1, e1, fma(kc, e0, fma(axx.mV2, g2, fma(axx.mV1, g1, mc * g0)))));
+          McM[f] = fma(2.0, e1, fma(mc, e0, -e2));
+          KcM[f] = fma(-8.0, e1, fma(kc, e0, e2));
+          MdM[f] = fma(2.0, g1, fma(mc, g0, -g2));
         }
       } else {
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-          const double c1 = qcV[f][1] + qcV[f][3], c0 = qcV[f][2], d1 = qdV[f][1] + qdV[f][3], d0 = qdV[f][2];
-          MxV[f] = fma(axx.mM1, c1, axx.mMc * c0);
-          KxV[f] = fma(axx.kM1, c1, fma(axx.kMc, c0, fma(axx.mM1, d1, axx.mMc * d0)));
-          const double e1 = qcM[f][1] + qcM[f][3], e0 = qcM[f][2], g1 = qdM[f][1] + qdM[f][3], g0 = qdM[f][2];
-          MxM[f] = fma(axx.mM1, e1, axx.mMc * e0);
-          KxM[f] = fma(axx.kM1, e1, fma(axx.kMc, e0, fma(axx.mM1, g1, axx.mMc * g0)));
+          const double c1 = qcV[f][1] + qcV[f][3], c16 = 16.0 * qcV[f][2], d1 = qdV[f][1] + qdV[f][3];
+          McV[f] = fma(2.0, c1, c16);
+          KcV[f] = fma(-8.0, c1, c16);
+          MdV[f] = fma(2.0, d1, 16.0 * qdV[f][2]);
+          const double e1 = qcM[f][1] + qcM[f][3], e16 = 16.0 * qcM[f][2], g1 = qdM[f][1] + qdM[f][3];
+          McM[f] = fma(2.0, e1, e16);
+          KcM[f] = fma(-8.0, e1, e16);
+          MdM[f] = fma(2.0, g1, 16.0 * qdM[f][2]);
         }
       }
       const long long node = (long long)io * plane + own;
@@ -1019,10 +1026,8 @@ __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FA
         double yV = 0.0, yM = 0.0;
 #pragma unroll
         for (int g = 0; g < NF; ++g) {
-          yV = fma(s.c.cK[f][g], KxV[g], yV);
-          yV = fma(s.c.cM[f][g], MxV[g], yV);
-          yM = fma(s.c.cK[f][g], KxM[g], yM);
-          yM = fma(s.c.cM[f][g], MxM[g], yM);
+          yV = fma(s.a1[f][g], KcV[g], fma(s.a2[f][g], MdV[g], fma(s.a3[f][g], McV[g], yV)));
+          yM = fma(s.a1[f][g], KcM[g], fma(s.a2[f][g], MdM[g], fma(s.a3[f][g], McM[g], yM)));
         }
         double* wo = s.w + (long long)f * s.field + node;
         dot = fma(cenV[f][0], yV, dot);
@@ -1054,19 +1059,6 @@ __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FA
       finish_reduction<Q2NT>(s.dot_partials, (int)gridDim.x, 1, s.fold.S, s.fold.hist, s.fold.post, 0, s.fold.ipc, sm.fin,
                              s.fold.ipc.ll == 3, FoldPre{sm.spre, &sm.seq_pre}, s.fold.xring);
   }
-}
-
-AxisQ2 axis_q2(int n_nodes, double h) {
-  AxisQ2 a{};
-  if (n_nodes == 1) {   // dummy axis of a 2-D mesh: M = [1], K = [0]
-    a.mVc[0] = a.mVc[1] = 1.0;
-    a.mMc = 1.0;
-    return a;
-  }
-  const double b = h / 30.0, q = 1.0 / (3.0 * h);
-  a.mV2 = -b; a.mV1 = 2 * b; a.mVc[0] = 8 * b; a.mVc[1] = 4 * b; a.mM1 = 2 * b; a.mMc = 16 * b;
-  a.kV2 = q; a.kV1 = -8 * q; a.kVc[0] = 14 * q; a.kVc[1] = 7 * q; a.kM1 = -8 * q; a.kMc = 16 * q;
-  return a;
 }
 
 void magic_div(unsigned d, unsigned long long* mag, unsigned* sh) {
@@ -1377,13 +1369,26 @@ static int launch_apply_q2(dpp_context* ctx, FusedState* F, int nf, const Coef& 
   const GridDesc& g = ctx->grid;
   const long long uplane = (long long)g.n[1] * g.n[2];
   Q2FArgs s{};
-  for (int d = 0; d < 3; ++d) {
-    s.n[d] = g.n[d];
-    s.ax[d] = axis_q2(g.n[d], ctx->uni_h[d]);
+  for (int d = 0; d < 3; ++d) s.n[d] = g.n[d];
+  {
+    // scale factors of the 1-D rows: mass h/30, stiffness 1/(3h); dummy axis of a 2-D mesh: M = [1], K = [0]
+    const bool dummy = g.n[0] == 1;
+    const double hx = ctx->uni_h[0], hy = ctx->uni_h[1], hz = ctx->uni_h[2];
+    const double bmx = dummy ? 1.0 : hx / 30.0, bkx = dummy ? 0.0 : 1.0 / (3.0 * hx);
+    const double B = (hy / 30.0) * (hz / 30.0);
+    s.rho_y = 10.0 / (hy * hy);
+    s.rho_z = 10.0 / (hz * hz);
+    s.cxM = dummy ? 1.0 : 4.0;
+    s.cxK = dummy ? 0.0 : 7.0;
+    for (int f = 0; f < 2; ++f)
+      for (int q = 0; q < 2; ++q) {
+        s.a1[f][q] = c.cK[f][q] * bkx * B;
+        s.a2[f][q] = c.cK[f][q] * bmx * B;
+        s.a3[f][q] = c.cM[f][q] * bmx * B;
+      }
   }
   s.pitch = F->pitch; s.plane = F->plane; s.field = F->field;
   s.r = F->buf[0]; s.pin = pin; s.pout = pout; s.w = F->buf[3];
-  s.c = c;
   s.dot_partials = ctx->d_partials;
   s.i_begin = (int)(ctx->owned_begin / uplane);
   s.i_end = (int)(ctx->owned_end / uplane);

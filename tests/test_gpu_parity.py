@@ -741,7 +741,8 @@ def test_q2_fused_cg_equals_unfused_sequence(cells, preset, monkeypatch):
         assert np.array_equal(u1, u1b) and s1.iteration_number == s1b.iteration_number
         if preset == "jacobi":
             assert s1.iteration_number == s2.iteration_number
-            assert np.allclose(i1.history, i2.history, rtol=1e-8, atol=0)
+            # (a residual at rounding level -- one free node: exact after two steps -- is noise, hence the atol)
+            assert np.allclose(i1.history, i2.history, rtol=1e-8, atol=1e-13 * i2.history[0])
         else:
             assert its_close(s1.iteration_number, s2.iteration_number)
         assert i1.converged_reason == i2.converged_reason
