@@ -17,6 +17,9 @@ if h.fused_cg_supported():
     nb = 2 * h.n_nodes * 8
     print(f"Q2 {N}^3 fused apply {fa:.4f} ms ({4*nb/fa/1e6:.0f} GB/s of 4 passes), r-update {fu:.4f} ms "
           f"({3*nb/fu/1e6:.0f} GB/s of 3 passes), plain apply {mv:.4f} ms")
+    ab, ub = h.time_cg_block_kernels(0, reps=10, warmup=3)
+    print(f"Q2 {N}^3 one-field block: fused apply {ab:.4f} ms ({2*nb/ab/1e6:.0f} GB/s of 4 passes), r-update {ub:.4f} ms "
+          f"({1.5*nb/ub/1e6:.0f} GB/s of 3 passes)")
 if "solve" in sys.argv:
     opt = h.default_options(); opt.max_it = 48
     _, info = h.solve(opt, want_solution=False)
