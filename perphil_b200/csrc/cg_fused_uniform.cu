@@ -811,7 +811,7 @@ struct __align__(16) SmemQ2 {
 
 // OCC = resident CTAs per SM the register budget is cut for: 3 for two fields (168 registers), 4 for the one-field
 // blocks of the Picard / fieldsplit solves (122 registers; measured at 128^3: 4 -> 1466 ms, 3 -> 1525 ms, 5 -> 1490 ms)
-template <int NF, int OCC, int TJ>
+template <int NF, int OCC, int TJ, bool PERSIST>
 __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FArgs s) {
   constexpr int Q2J = TJ, Q2NT = Q2PT * TJ, Q2SLOT = SmemQ2<NF, TJ>::SLOT;
   extern __shared__ __align__(16) unsigned char smem_raw_q2[];
@@ -829,13 +829,32 @@ __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FA
 
   const int ni = s.n[0], nj = s.n[1], nk = s.n[2], pitch = s.pitch;
   const int ntiles = s.ntj * s.ntk;
-  const int tile = blockIdx.x % ntiles, seg = blockIdx.x / ntiles;
+  const int nown = s.i_end - s.i_begin;
+  const int warp = tid >> 5, lane = tid & 31;
+  double dot = 0.0;
+  // Work = (tile, plane) steps.  nseg > 0: one (tile, x-segment) item per CTA, tile index fastest (neighbouring tiles
+  // run side by side: their halo rows hit in L2).  nseg == 0 (thin slabs: few planes, CTA count not a multiple of the
+  // resident slots): equal contiguous shares of the steps per CTA, processed as runs of consecutive planes of one tile.
+  // (PERSIST is a template parameter: the one-run variant compiles without the loop -- it is 6 % faster that way)
+  long long wbeg, wend;
+  if (!PERSIST) {
+    const int tile_ = blockIdx.x % ntiles, seg_ = blockIdx.x / ntiles;
+    wbeg = (long long)tile_ * nown + bstart(seg_, nown, s.nseg);
+    wend = (long long)tile_ * nown + bstart(seg_ + 1, nown, s.nseg);
+  } else {
+    const long long total = (long long)ntiles * nown;
+    wbeg = (total * blockIdx.x) / gridDim.x;
+    wend = (total * (blockIdx.x + 1)) / gridDim.x;
+  }
+#pragma unroll 1
+  do {
+  const int tile = PERSIST ? (int)(wbeg / nown) : (int)(blockIdx.x % ntiles);
+  const int run_a = (int)(wbeg - (long long)tile * nown);
+  const int run_len = (int)((wend - wbeg) < (long long)(nown - run_a) ? (wend - wbeg) : (long long)(nown - run_a));
+  wbeg += run_len;
   const int tkid = tile % s.ntk, tjid = tile / s.ntk;
   const int k0 = tkid * Q2K, j0 = tjid * Q2J;            // even: node parity = local parity
-  const int nown = s.i_end - s.i_begin;
-  const int i_lo = s.i_begin + bstart(seg, nown, s.nseg);
-  const int i_hi = s.i_begin + bstart(seg + 1, nown, s.nseg);
-  const int warp = tid >> 5, lane = tid & 31;
+  const int i_lo = s.i_begin + run_a, i_hi = i_lo + run_len;
   const int jr = warp + (TJ / 2) * (lane >> 4);        // rows {w, w + TJ / 2} of a warp have one parity
   const int kp = 2 * (lane & 15);
   const int j = j0 + jr, k = k0 + kp;
@@ -880,7 +899,6 @@ __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FA
 #pragma unroll
     for (int d = 0; d < 3; ++d) cenV[f][d] = cenM[f][d] = 0.0;
   }
-  double dot = 0.0;
   const int i_first = i_lo - Q2H;
   const long long own = (long long)j * pitch + k;
 
@@ -918,7 +936,7 @@ __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FA
     d2M = fma(MYR, uzM, d2M);                                                                         \
   }
 
-  __syncthreads();   // dtab, spre
+  __syncthreads();   // dtab, spre; later runs: the plane ring is free (every thread finished the previous run)
   issue(i_first, 0);
   issue(i_first + 1, 1);
   int slot = 0;
@@ -1041,8 +1059,9 @@ __global__ void __launch_bounds__(Q2PT * TJ, OCC) k_cg_fused_apply_q2(const Q2FA
     }
     if (++slot == Q2RING) slot = 0;
   }
-#undef DPP_Q2F_ROW
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  } while (PERSIST && wbeg < wend);  // runs
+#undef DPP_Q2F_ROW
 
   if (s.dot_partials != nullptr) {
 #pragma unroll
@@ -1411,18 +1430,40 @@ static int launch_apply_q2(dpp_context* ctx, FusedState* F, int nf, const Coef& 
     ctx->set_error("fused CG (degree 2): plane too wide for the partials scratch");
     return DPP_ERR_INVALID;
   }
-  s.nseg = choose_x_segments(tiles, nown, ctx->sm_count * (nf == 1 ? OCC1 : 3), kMaxPartialBlocks, 2 * Q2H);
-  if (const char* e = getenv("DPP_FUSED_SCHED"))
-    if (atoi(e) > 0 && (long long)tiles * atoi(e) <= kMaxPartialBlocks) s.nseg = std::min(atoi(e), nown);
+  const int capacity = ctx->sm_count * (nf == 1 ? OCC1 : 3);
+  s.nseg = choose_x_segments(tiles, nown, capacity, kMaxPartialBlocks, 2 * Q2H);
+  {
+    // Thin slabs (N > 1: a few dozen planes per rank): tiles x segments is a small non-integer number of waves of the
+    // resident slots and every segment pays 4 redundant planes.  Equal shares of the (tile, plane) steps per resident
+    // CTA fill the last wave; taken when the step model says >= 10 % fewer plane steps and neighbouring tiles still
+    // run within a few planes of each other (their halo rows then hit in L2: the in-flight footprint between the two
+    // visits, offset x resident CTAs x tile bytes, stays well inside the 126 MB).
+    const int len = (nown + s.nseg - 1) / s.nseg;
+    const long long rounds = ((long long)tiles * s.nseg + capacity - 1) / capacity;
+    const double cost_seg = (double)rounds * (len + 2 * Q2H + 2 + (len > 32 ? (len - 32) / 4 : 0));
+    const double spc = std::ceil((double)tiles * nown / capacity);
+    const double cost_per = spc + (1.0 + spc / nown) * (2 * Q2H + 2);
+    const double off = std::fabs(nown - spc * std::max(1.0, std::floor(nown / spc + 0.5)));
+    const double between = off * capacity * ((8.0 + 2 * Q2H) * Q2ROW * 16.0 * nf);
+    if (cost_per < 0.9 * cost_seg && between < 32e6 && (long long)tiles * nown >= 4LL * capacity) s.nseg = 0;
+  }
+  if (const char* e = getenv("DPP_FUSED_SCHED")) {   // measurement override: "p" persistent, "<n>" segments
+    if (e[0] == 'p') s.nseg = 0;
+    else if (atoi(e) > 0 && (long long)tiles * atoi(e) <= kMaxPartialBlocks) s.nseg = std::min(atoi(e), nown);
+  }
   static bool attr = false;
   if (!attr) {
-    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<2, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<2, 8>)));
-    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<1, OCC1, TJ1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<1, TJ1>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<2, 3, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<2, 8>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<2, 3, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<2, 8>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<1, OCC1, TJ1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<1, TJ1>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply_q2<1, OCC1, TJ1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemQ2<1, TJ1>)));
     attr = true;
   }
-  const dim3 grid(tiles * s.nseg), block(Q2PT * tj);
-  if (nf == 2) DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<2, 3, 8>, grid, block, sizeof(SmemQ2<2, 8>), ctx->stream, s));
-  else DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<1, OCC1, TJ1>, grid, block, sizeof(SmemQ2<1, TJ1>), ctx->stream, s));
+  const dim3 grid(s.nseg > 0 ? tiles * s.nseg : (unsigned)std::min<long long>(capacity, (long long)tiles * nown)), block(Q2PT * tj);
+  if (nf == 2 && s.nseg > 0) DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<2, 3, 8, false>, grid, block, sizeof(SmemQ2<2, 8>), ctx->stream, s));
+  else if (nf == 2) DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<2, 3, 8, true>, grid, block, sizeof(SmemQ2<2, 8>), ctx->stream, s));
+  else if (s.nseg > 0) DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<1, OCC1, TJ1, false>, grid, block, sizeof(SmemQ2<1, TJ1>), ctx->stream, s));
+  else DPP_CUDA(launch_pdl(k_cg_fused_apply_q2<1, OCC1, TJ1, true>, grid, block, sizeof(SmemQ2<1, TJ1>), ctx->stream, s));
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
   *n_partial_blocks = (int)grid.x;

@@ -37,6 +37,7 @@ def _spawn(nproc, args, env_extra=None, timeout=600):
 
 
 @pytest.mark.parametrize("size,degree,env", [(32, 1, {}), (32, 1, {"DPP_NO_IPC": "1"}), (12, 2, {}), (20, 2, {}),
+                                             (20, 2, {"DPP_FUSED_SCHED": "p"}),   # equal-share partition on slabs
                                              (12, 2, {"DPP_NO_IPC": "1"})])
 def test_two_rank_slab_solves_equal_single_gpu(size, degree, env):
     if _gpus() < 2:
@@ -46,7 +47,7 @@ def test_two_rank_slab_solves_equal_single_gpu(size, degree, env):
     assert "MGPU OK" in out.stdout, out.stdout[-3000:]
     # peer_memory bits: 1 mailbox all-reduce, 2 fused-CG halo push (uniform grids, Q1 and Q2), 4 halo inboxes for
     # generic vectors
-    want_ipc = "ipc=0" if env else "ipc=7"
+    want_ipc = "ipc=0" if "DPP_NO_IPC" in env else "ipc=7"
     assert want_ipc in out.stdout, out.stdout[-2000:]
 
 

@@ -761,6 +761,32 @@ def test_q2_fused_cg_equals_unfused_sequence(cells, preset, monkeypatch):
     pb.release_handles()
 
 
+@pytest.mark.parametrize("cells", [(20, 17, 33), (3, 30, 40), (40, 9)])
+def test_q2_fused_cg_persistent_partition(cells, monkeypatch):
+    """The equal-share partition of the (tile, plane) steps (thin slabs; forced here with DPP_FUSED_SCHED=p), where a
+    CTA processes several runs -- the tail of one tile and the head of the next -- gives the iteration counts and the
+    solution of the one-segment-per-CTA launch."""
+    W, p, bcs, _ = make_problem(cells, 2)
+    params = {**pb.B200_CG_JACOBI_PARAMS, "b200_history": 8192}
+    monkeypatch.setenv("DPP_FUSED_SCHED", "1")
+    s1, u1, i1 = _solve_vec(W, p, bcs, params)
+    monkeypatch.setenv("DPP_FUSED_SCHED", "p")
+    s2, u2, i2 = _solve_vec(W, p, bcs, params)
+    s2b, u2b, _ = _solve_vec(W, p, bcs, params)
+    monkeypatch.delenv("DPP_FUSED_SCHED", raising=False)
+    assert s1.iteration_number == s2.iteration_number == s2b.iteration_number
+    assert np.allclose(i1.history, i2.history, rtol=1e-8, atol=1e-13 * i1.history[0])
+    assert rel_err(u2, u1) < 1e-9 and np.array_equal(u2, u2b)
+    n1 = pb.solve_dpp_nonlinear(W, p, bcs, solver_parameters=pb.B200_PICARD_SPLIT_PARAMS)
+    v1 = np.concatenate([n1.solution.sub(0).dat.data, n1.solution.sub(1).dat.data])
+    monkeypatch.setenv("DPP_FUSED_SCHED", "p")
+    n2 = pb.solve_dpp_nonlinear(W, p, bcs, solver_parameters=pb.B200_PICARD_SPLIT_PARAMS)
+    v2 = np.concatenate([n2.solution.sub(0).dat.data, n2.solution.sub(1).dat.data])
+    monkeypatch.delenv("DPP_FUSED_SCHED", raising=False)
+    assert its_close(n1.iteration_number, n2.iteration_number) and rel_err(v1, v2) < 1e-7
+    pb.release_handles()
+
+
 def test_q2_block_picard_config4_shape():
     """BASELINE configs[3] at a size the oracle reaches: Q2 hexes, scale-splitting Picard, 6 outer iterations."""
     W, p, bcs, osys = make_problem((6, 6, 6), 2)
