@@ -473,8 +473,8 @@ int dpp_comm_ipc_export(dpp_handle ctx, void* blob_out) {
   dpp::Comm* C = ctx->comm;
   if (C && ctx->world > 1 && ctx->world <= dpp::kMaxIpcRanks && !getenv("DPP_NO_IPC")) {
     if (!C->mbox) {
-      DPP_CHECK(dpp::dev_alloc(ctx, &C->mbox, 2 * dpp::kMaxIpcRanks * dpp::kMboxWords + 2));
-      DPP_CUDA(cudaMemset(C->mbox, 0, sizeof(double) * (2 * dpp::kMaxIpcRanks * dpp::kMboxWords + 2)));
+      DPP_CHECK(dpp::dev_alloc(ctx, &C->mbox, (int64_t)dpp::kMboxDoubles));
+      DPP_CUDA(cudaMemset(C->mbox, 0, sizeof(double) * dpp::kMboxDoubles));
       DPP_CUDA(cudaDeviceSynchronize());   // the zeros are in place before any peer can learn the handle
     }
     if (cudaIpcGetMemHandle(&b.mbox_handle, C->mbox) == cudaSuccess) b.valid |= 1;

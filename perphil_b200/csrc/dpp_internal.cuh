@@ -229,6 +229,12 @@ void cg_fused_destroy(dpp_context* ctx);
 constexpr int kMaxIpcRanks = 16;
 constexpr int kMboxEntry = 8;      // doubles per mailbox entry: 7 values + sequence flag
 constexpr int kMboxWords = 16;     // 8-byte words per entry: tagged-word protocol = 2 words per value (cg_device.cuh)
+// wide entries behind the narrow ones and the sequence counter (same allocation, same IPC handle): the classical
+// Gram-Schmidt dot products of GMRES(30), up to 32 values per reduction (vector_ops.cu: k_reduce_partials_wide)
+constexpr int kMboxWideVals = 32;
+constexpr int kMboxWideWords = 2 * kMboxWideVals;
+constexpr size_t kMboxWideOffset = 2 * (size_t)kMaxIpcRanks * kMboxWords + 2;
+constexpr size_t kMboxDoubles = kMboxWideOffset + 2 * (size_t)kMaxIpcRanks * kMboxWideWords;
 struct IpcReduce {                 // kernel argument of the mailbox allreduce
   double* local;                   // [2 slots][world][kMboxWords]
   double* peer[kMaxIpcRanks];      // the same array of every rank (peer[rank] == local)

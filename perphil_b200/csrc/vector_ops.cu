@@ -47,6 +47,80 @@ __global__ void __launch_bounds__(VT) k_reduce_partials_ipc(const double* __rest
   finish_reduction(partials, nblocks, width, S, hist, post, out_offset, ipc, sm);
 }
 
+// The same all-reduce for up to kMboxWideVals values (GMRES(30): the j + 1 <= 31 dot products of one classical
+// Gram-Schmidt pass).  Tagged words as in finish_reduction (value = flag: two 8-byte words per value, the upper halves
+// carry the sequence number), but one THREAD per (peer, value): the 2 x 31 x world remote stores and the polls of the
+// own mailbox run side by side, so a wide exchange costs about what a one-value exchange costs.  Shares the sequence
+// counter with the narrow mailboxes (every rank runs the same sequence of exchanges, narrow and wide alike).
+__global__ void __launch_bounds__(VT) k_reduce_partials_wide(const double* __restrict__ partials, int nblocks, int width,
+                                                              double* S, double* hist, int post, int out_offset,
+                                                              IpcReduce ipc) {
+  __shared__ double sm[VT / 32];
+  __shared__ double vals[kMboxWideVals];
+  __shared__ double recv[kMaxIpcRanks][kMboxWideVals];
+  __shared__ unsigned long long seq_sm;
+  __shared__ int timed_out;
+  const int tid = threadIdx.x;
+  for (int w = 0; w < width; ++w) {
+    double v = 0.0;
+    for (int b = tid; b < nblocks; b += VT) v += partials[(size_t)b * width + w];
+    const double t = block_sum(v, sm);
+    if (tid == 0) vals[w] = t;
+  }
+  if (tid == 0) {
+    timed_out = 0;
+    seq_sm = *ipc.seq_dev + 1;
+    *ipc.seq_dev = seq_sm;
+  }
+  __syncthreads();
+  const unsigned long long seq = seq_sm;
+  const int slot = (int)(seq & 1ull);
+  const unsigned long long tag = (seq & 0xffffffffull) << 32;
+  const int items = ipc.world * width;
+  const long long t0 = clock64();
+  // every storing thread orders what this rank wrote before (and what it observed) ahead of its mailbox words
+  if (tid < items) asm volatile("fence.acq_rel.sys;" ::: "memory");
+  for (int it = tid; it < items; it += VT) {
+    const int peer = it % ipc.world, w = it / ipc.world;
+    const size_t mine = kMboxWideOffset + ((size_t)slot * ipc.world + ipc.rank) * kMboxWideWords;
+    volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(ipc.peer[peer]) + mine;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[w]);
+    dst[2 * w] = tag | (bits & 0xffffffffull);
+    dst[2 * w + 1] = tag | (bits >> 32);
+  }
+  for (int it = tid; it < items; it += VT) {
+    const int peer = it % ipc.world, w = it / ipc.world;
+    const size_t theirs = kMboxWideOffset + ((size_t)slot * ipc.world + peer) * kMboxWideWords;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(ipc.local) + theirs;
+    unsigned long long lo, hi;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(lo) : "l"(src + 2 * w) : "memory");
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(hi) : "l"(src + 2 * w + 1) : "memory");
+      if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+      if (clock64() - t0 > 60000000000LL) {  // ~30 s: a peer died; report instead of hanging the GPU
+        timed_out = 1;
+        break;
+      }
+    }
+    recv[peer][w] = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+  }
+  __syncthreads();
+  if (timed_out) {
+    if (tid == 0) S[S_REASON] = (double)DPP_DIVERGED_COMM_TIMEOUT;
+    return;
+  }
+  if (tid < width) {   // rank order: every rank adds the same numbers in the same order
+    double t = 0.0;
+    for (int r = 0; r < ipc.world; ++r) t += recv[r][tid];
+    S[S_TMP + out_offset + tid] = t;
+  }
+  __syncthreads();
+  if (tid == 0 && post != POST_NONE) {
+    __threadfence();
+    apply_post(S, hist, post);
+  }
+}
+
 __global__ void __launch_bounds__(VT) k_axpby(VecLayout L, double a, const double* x, double b, double* y) {
   const Chunk c = my_chunk(L);
   for (long long i = c.begin + threadIdx.x; i < c.end; i += VT) {
@@ -286,6 +360,16 @@ int reduce_partials(dpp_context* ctx, int nblocks, int width, int slot, PostOp p
     ctx->launches++;
     DPP_CUDA(cudaGetLastError());
     return DPP_OK;
+  }
+  if (dist && comm_ipc_ready(ctx) && width <= kMboxWideVals) {
+    const IpcReduce ipc = comm_ipc_reduce_args(ctx);
+    if (ipc.world > 1 && (ipc.ll == 1 || ipc.ll == 3)) {   // tagged-word protocol only; else NCCL below
+      k_reduce_partials_wide<<<1, VT, 0, ctx->stream>>>(ctx->d_partials, nblocks, width, S, hist_device(ctx, slot),
+                                                        (int)post, out_offset, ipc);
+      ctx->launches++;
+      DPP_CUDA(cudaGetLastError());
+      return DPP_OK;
+    }
   }
   k_reduce_partials<<<1, VT, 0, ctx->stream>>>(ctx->d_partials, nblocks, width, S, hist_device(ctx, slot), (int)post,
                                                dist ? 0 : 1, out_offset);
