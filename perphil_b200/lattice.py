@@ -60,6 +60,10 @@ def detect_lattice(dim: int, degree: int, cell_node_map: np.ndarray, node_coords
         i_d[order] = group
         naxes.append(cs[new])
         idx.append(i_d)
+        # every other axis of a lattice has at least p + 1 node planes: more distinct coordinates than
+        # n / (p + 1)^(dim - 1) on one axis (a distorted mesh has ~n) cannot be one -- skip the remaining sorts
+        if naxes[-1].size * (p + 1) ** (dim - 1) > n:
+            return None
     counts = [a.size for a in naxes]
     if int(np.prod(counts)) != n or any((c - 1) % p for c in counts) or any(c < p + 1 for c in counts):
         return None
