@@ -1387,6 +1387,10 @@ static int launch_apply_q2(dpp_context* ctx, FusedState* F, int nf, const Coef& 
                            int slot, const double* dtab, int* n_partial_blocks) {
   const GridDesc& g = ctx->grid;
   const long long uplane = (long long)g.n[1] * g.n[2];
+  if (ctx->owned_begin % uplane || ctx->owned_end % uplane) {
+    ctx->set_error("fused CG: owned range must consist of whole x-planes");
+    return DPP_ERR_INVALID;
+  }
   Q2FArgs s{};
   for (int d = 0; d < 3; ++d) s.n[d] = g.n[d];
   {
