@@ -74,6 +74,16 @@ struct FArgs {
   int dom_lo, dom_hi;        // local plane 0 / n[0]-1 lies on the domain boundary (else it is a ghost plane)
   int defer_x;               // x is updated by the r-update kernel from the direction ring, not here
   FoldArgs fold;             // <p,Ap> reduction epilogue run by the last CTA
+  // MODE 1 with no_w: w = A p is not stored (the MODE 2 kernel that follows recomputes it).
+  // MODE 2 (r-update with the stencil in it): r <- r - alpha A p on the computed nodes, z = D^-1 r, <r,z>, <z,z>
+  int no_w;
+  double* r;                 // residual, padded (MODE 2: read through tm_x tiles, written here)
+  double* partials2;         // [blocks][2]
+  IpcHalo halo;              // peer residual vectors: the first / last owned plane is stored there as well
+  int own_first, own_last;   // first / last owned plane of the slab (halo push), -1: no neighbour on that side
+  long long ob, oe;          // owned padded range (deferred x accumulation)
+  const double* pr[kXRing];  // direction ring
+  const double* xring;       // step lengths of the ring
 };
 
 __device__ __forceinline__ int bstart(int t, int n, int nt) { return (int)(((long long)t * n) / nt); }
@@ -121,9 +131,13 @@ struct __align__(128) Smem {
   int last_flag;
 };
 
-// FUSED = true : CG iteration kernel (p = dinv r + beta p_old formed on chip, deferred x update, p stored)
-// FUSED = false: plain apply w = A p on padded vectors (tm_p = input), optional <p, w>
-template <int NF, bool FUSED>
+// MODE 1: CG iteration kernel (p = dinv r + beta p_old formed on chip, deferred x update, p stored)
+// MODE 0: plain apply w = A p on padded vectors (tm_p = input), optional <p, w>
+// MODE 2: residual update with the stencil in it: w = A p is RECOMPUTED from the direction the MODE 1 kernel stored
+//         (tm_p) instead of being written there and read here -- one vector pass less per iteration, the same bits --
+//         r (tiles through tm_x) <- r - alpha w, z = D^-1 r in registers, <r,z>, <z,z> + KSPCG bookkeeping, halo push,
+//         and every 15th launch the deferred x accumulation.  Class-mask handles only (computed nodes = free nodes).
+template <int NF, int MODE>
 __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const __grid_constant__ CUtensorMap tm_r,
                                                           const __grid_constant__ CUtensorMap tm_p,
                                                           const __grid_constant__ CUtensorMap tm_x) {
@@ -131,6 +145,7 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem<NF>& sm = *reinterpret_cast<Smem<NF>*>(smem_raw);
   constexpr int RS = Smem<NF>::RS;
+  constexpr bool FUSED = MODE == 1, RUPD = MODE == 2;
 
   const int ni = s.n[0], nj = s.n[1], nk = s.n[2];
   const int nown = s.i_end - s.i_begin;
@@ -149,8 +164,8 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
   // the previous kernel of the stream is still in its reduction epilogue
   if (tid < 16) sm.dtab[tid] = (FUSED && tid < 8 * NF) ? s.dtab[(tid >> 3) * kClsPerField + (tid & 7)] : 1.0;
   pdl_wait();  // everything below reads what the previous kernel of the stream produced
-  if (FUSED && s.S[S_REASON] != 0.0) return;
-  if (FUSED && s.fold.enabled) {
+  if ((FUSED || RUPD) && s.S[S_REASON] != 0.0) return;
+  if ((FUSED || RUPD) && s.fold.enabled) {
     if (tid < kPreScalars) sm.spre[tid] = s.fold.S[tid];
     if (tid == kPreScalars && s.fold.ipc.world > 1) sm.seq_pre = *s.fold.ipc.seq_dev;
   }
@@ -162,7 +177,8 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     xpend = !s.defer_x && s.S[S_XPEND] != 0.0;
     alpha_prev = xpend ? s.S[S_ALPHA] : 0.0;
   }
-  double dot = 0.0;
+  const double alpha_r = RUPD ? s.S[S_ALPHA] : 0.0;
+  double dot = 0.0, srz = 0.0, szz = 0.0;
   unsigned phase = 0;  // bit q = parity of the next completion of ring slot q
   const long long plane = s.plane;
   const int pitch = s.pitch;
@@ -203,7 +219,7 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     // producer (one thread): fetch plane PL into ring slot SL
 #define DPP_ISSUE(SL, PL)                                                                              \
   if (tid == 0) {                                                                                      \
-    const bool xin = FUSED && xpend && (PL) >= i_lo && (PL) < i_hi;                                    \
+    const bool xin = ((FUSED && xpend) || RUPD) && (PL) >= i_lo && (PL) < i_hi;                        \
     const unsigned mb = mbar0 + 8 * (SL);                                                              \
     fence_proxy_async();                                                                               \
     mbar_expect_tx(mb, (unsigned)((FUSED ? 2 : 1) * NF * SLOT * 8 + (xin ? NF * XSLOT * 8 : 0)));      \
@@ -264,6 +280,12 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     const double mxo = s.mo[0], kxo = s.ko[0];
 
     double qc[NF][2][3], qd[NF][2][3], prev_cen[NF][2];
+    double rprev[NF][2], d0[NF];   // MODE 2: r of the output plane (tile read one step earlier); free-node D^-1
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      rprev[f][0] = rprev[f][1] = 0.0;
+      d0[f] = RUPD ? s.dtab[f * kClsPerField] : 0.0;
+    }
 #pragma unroll
     for (int f = 0; f < NF; ++f)
 #pragma unroll
@@ -289,7 +311,14 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
   {                                                                                                   \
     mbar_wait(mbar0 + 8 * (C), (phase >> (C)) & 1u);                                                  \
     phase ^= 1u << (C);                                                                               \
-    double cen[NF][2];                                                                                \
+    double cen[NF][2], rcur[NF][2];                                                                   \
+    _Pragma("unroll") for (int f = 0; f < NF; ++f) {                                                  \
+      rcur[f][0] = rcur[f][1] = 0.0;                                                                  \
+      if (RUPD && ip >= i_lo && ip < i_hi) {                                                          \
+        rcur[f][0] = sm.x[C][f * XSLOT + xown_e];                                                     \
+        rcur[f][1] = sm.x[C][f * XSLOT + xown_e + TK];                                                \
+      }                                                                                               \
+    }                                                                                                 \
     if (FUSED) {                                                                                      \
       const bool pbnd = ni > 1 && ((ip == 0 && s.dom_lo) || (ip == ni - 1 && s.dom_hi));              \
       const bool pwr = ip >= pw_lo && ip < pw_hi;                                                     \
@@ -357,14 +386,29 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
           yv = fma(s.c.cM[f][g], Mx[g][r], yv);                                                       \
         }                                                                                             \
         if (r == 0 ? actA : actB) {                                                                   \
-          s.w[f * s.field + off_c - plane + r * pitch] = yv;                                          \
-          dot = fma(prev_cen[f][r], yv, dot);                                                         \
+          if (RUPD) {                                                                                 \
+            const long long q = off_c - plane + r * pitch;                                            \
+            const double rn = fma(-alpha_r, yv, rprev[f][r]);                                         \
+            s.r[f * s.field + q] = rn;                                                                \
+            const int io = ip - 1;                                                                    \
+            const long long inpl = q - (long long)io * plane;                                         \
+            if (io == s.own_first) s.halo.peer_r[0][f * s.halo.peer_field[0] + s.halo.peer_ghost_off[0] + inpl] = rn; \
+            if (io == s.own_last) s.halo.peer_r[1][f * s.halo.peer_field[1] + s.halo.peer_ghost_off[1] + inpl] = rn;  \
+            const double z = d0[f] * rn;                                                              \
+            srz = fma(rn, z, srz);                                                                    \
+            szz = fma(z, z, szz);                                                                     \
+          } else {                                                                                    \
+            if (!(FUSED && s.no_w)) s.w[f * s.field + off_c - plane + r * pitch] = yv;                \
+            dot = fma(prev_cen[f][r], yv, dot);                                                       \
+          }                                                                                           \
         }                                                                                             \
       }                                                                                               \
     }                                                                                                 \
     _Pragma("unroll") for (int f = 0; f < NF; ++f) {                                                  \
       prev_cen[f][0] = cen[f][0];                                                                     \
       prev_cen[f][1] = cen[f][1];                                                                     \
+      rprev[f][0] = rcur[f][0];                                                                       \
+      rprev[f][1] = rcur[f][1];                                                                       \
     }                                                                                                 \
     off_c += plane;                                                                                   \
   }
@@ -383,6 +427,66 @@ __global__ void __launch_bounds__(NT, 2) k_cg_fused_apply(const FArgs s, const _
     // nothing is in flight here: every fetched plane was consumed, so the per-slot parity bits stay valid
   }  // runs
 
+  if (RUPD) {
+    if (s.defer_x) {
+      // deferred x update (same rule and arithmetic as in k_cg_r_update): after every 15th iteration the fifteen
+      // pending directions are added in iteration order; flat partition of the owned range over the CTAs
+      const int kit = (int)s.S[S_ITS];
+      if ((kit + 1) % (kXRing - 1) == 0) {
+        constexpr int NDIR = kXRing - 1, CH = 8;
+        const long long nown2 = (s.oe - s.ob) / 2;
+        const long long b2 = (nown2 * blockIdx.x) / gridDim.x, e2 = (nown2 * (blockIdx.x + 1)) / gridDim.x;
+#pragma unroll 1
+        for (int f = 0; f < NF; ++f) {
+          double* xf = s.x + (long long)f * s.field;
+          const long long foff = (long long)f * s.field;
+          for (long long t = b2 + tid; t < e2; t += NT) {
+            const long long qq = s.ob + 2 * t;
+            double2 xv = *reinterpret_cast<const double2*>(xf + qq);
+#pragma unroll
+            for (int c0 = 0; c0 < NDIR; c0 += CH) {
+              double2 pv[CH];
+              double al[CH];
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (c0 + j < NDIR) {
+                  const int slot = (kit - (NDIR - 1) + c0 + j + 1) % kXRing;
+                  al[j] = s.xring[slot];
+                  pv[j] = *reinterpret_cast<const double2*>(s.pr[slot] + foff + qq);
+                }
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (c0 + j < NDIR) {
+                  xv.x = fma(al[j], pv[j].x, xv.x);
+                  xv.y = fma(al[j], pv[j].y, xv.y);
+                }
+            }
+            *reinterpret_cast<double2*>(xf + qq) = xv;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      srz += __shfl_xor_sync(0xffffffffu, srz, o);
+      szz += __shfl_xor_sync(0xffffffffu, szz, o);
+    }
+    __syncthreads();   // sm.red / sm.fin are free
+    if (tx == 0) { sm.red[ty] = srz; sm.fin[ty] = szz; }
+    __syncthreads();
+    if (tid == 0) {
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int w = 0; w < TY; ++w) { t0 += sm.red[w]; t1 += sm.fin[w]; }
+      s.partials2[(size_t)blockIdx.x * 2] = t0;
+      s.partials2[(size_t)blockIdx.x * 2 + 1] = t1;
+    }
+    const bool remote = s.halo.peer_r[0] != nullptr || s.halo.peer_r[1] != nullptr;
+    if (s.fold.enabled && last_block_arrives(s.fold.counter, gridDim.x, &sm.last_flag))
+      finish_reduction(s.partials2, (int)gridDim.x, 2, s.fold.S, s.fold.hist, s.fold.post, 0, s.fold.ipc, sm.fin, remote,
+                       FoldPre{sm.spre, &sm.seq_pre});
+    return;
+  }
   if (s.dot_partials != nullptr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -1113,6 +1217,7 @@ struct FusedState {
   long long plane = 0, field = 0;
   double* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // r, p0, p1, w, x  (2 * field doubles each)
   CUtensorMap tm[2][4];   // [nf-1][r, p0, p1, x]
+  CUtensorMap tm_rx[2];   // [nf-1] r without halo (the tiles the stencil r-update reads)
   int32_t* bc_pad[2] = {nullptr, nullptr};
   long long bc_count[2] = {0, 0};
   long long bc_cap[2] = {0, 0};
@@ -1216,6 +1321,7 @@ static int fused_state(dpp_context* ctx, FusedState** out) {
       DPP_CHECK(make_map(ctx, F, &F->tm[nf - 1][1], F->buf[1], nf, true));
       DPP_CHECK(make_map(ctx, F, &F->tm[nf - 1][2], F->buf[2], nf, true));
       DPP_CHECK(make_map(ctx, F, &F->tm[nf - 1][3], F->buf[4], nf, false));
+      DPP_CHECK(make_map(ctx, F, &F->tm_rx[nf - 1], F->buf[0], nf, false));
     }
   }
   *out = ctx->fused;
@@ -1261,7 +1367,10 @@ static void decide_defer_x(dpp_context* ctx, FusedState* F) {
 }
 
 // variant of the fused iteration the launches of the current solve use (part of the CUDA-graph key of a CG batch)
-int cg_fused_variant(dpp_context* ctx) { return (ctx->fused != nullptr && ctx->fused->defer) ? 1 : 0; }
+int cg_fused_variant(dpp_context* ctx) {
+  if (ctx->fused == nullptr || !ctx->fused->defer) return 0;
+  return getenv("DPP_NO_STENCIL_RUPD") != nullptr ? 1 : 2;
+}
 
 // launch with programmatic stream serialization allowed (the kernel calls griddepcontrol.wait itself)
 template <typename... KArgs, typename... Args>
@@ -1291,9 +1400,11 @@ static FoldArgs fold_args(dpp_context* ctx, int slot, int post, int counter) {
   return f;
 }
 
-static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, const Coef& c, const CUtensorMap& tm_pin,
+// mode: 0 plain apply, 1 fused CG iteration kernel, 2 residual update with the stencil in it (see the kernel)
+static int launch_apply(dpp_context* ctx, FusedState* F, int nf, int mode, const Coef& c, const CUtensorMap& tm_pin,
                         double* pout, int slot, const double* dtab, bool want_dot, int* n_partial_blocks,
-                        bool interior_only = false, bool defer_x = false) {
+                        bool interior_only = false, bool defer_x = false, bool no_w = false) {
+  const bool fused = mode != 0;
   const GridDesc& g = ctx->grid;
   const long long uplane = (long long)g.n[1] * g.n[2];
   if (ctx->owned_begin % uplane || ctx->owned_end % uplane) {
@@ -1316,9 +1427,23 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
   s.S = fused ? ctx->d_scalars + (size_t)slot * S_SLOT_SIZE : nullptr;
   s.dtab = dtab;
   s.dom_lo = ctx->dom_lo; s.dom_hi = ctx->dom_hi;
-  if (fused) s.fold = fold_args(ctx, slot, POST_CG_PAP, 0);
+  if (mode == 1) s.fold = fold_args(ctx, slot, POST_CG_PAP, 0);
   s.defer_x = defer_x ? 1 : 0;
-  if (defer_x) s.fold.xring = F->d_xring;
+  if (defer_x && mode == 1) s.fold.xring = F->d_xring;
+  s.no_w = no_w ? 1 : 0;
+  s.own_first = s.own_last = -1;
+  if (mode == 2) {
+    s.fold = fold_args(ctx, slot, POST_CG_RZ, 1);
+    s.r = F->buf[0];
+    s.partials2 = ctx->d_partials;
+    s.halo = comm_ipc_halo(ctx);
+    if (s.halo.peer_r[0] != nullptr) s.own_first = s.i_begin;
+    if (s.halo.peer_r[1] != nullptr) s.own_last = s.i_end - 1;
+    s.ob = (long long)s.i_begin * F->plane;
+    s.oe = (long long)s.i_end * F->plane;
+    for (int j = 0; j < kXRing; ++j) s.pr[j] = F->pring[j];
+    s.xring = F->d_xring;
+  }
   s.j_lo = 0; s.j_hi = g.n[1]; s.k_lo = 0; s.k_hi = g.n[2];
   if (fused && interior_only && g.n[1] >= 3 && g.n[2] >= 3 && (g.n[0] >= 3 || g.n[0] == 1)) {
     // class-mask mode: every domain-boundary node is a constrained row whose p, w, x stay zero and whose
@@ -1361,20 +1486,25 @@ static int launch_apply(dpp_context* ctx, FusedState* F, int nf, bool fused, con
     }
   }
   if (!F->attr_set) {
-    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<2>)));
-    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
-    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<2>)));
-    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<2>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<2>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<2>)));
+    DPP_CUDA(cudaFuncSetAttribute(k_cg_fused_apply<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
     F->attr_set = true;
   }
   dim3 grid(nctas), block(TK, TY);
   const CUtensorMap* T = F->tm[nf - 1];
+  const CUtensorMap& tm_rx = F->tm_rx[nf - 1];
   if (nf == 2) {
-    if (fused) DPP_CUDA(launch_pdl(k_cg_fused_apply<2, true>, grid, block, sizeof(Smem<2>), ctx->stream, s, T[0], tm_pin, T[3]));
-    else k_cg_fused_apply<2, false><<<grid, block, sizeof(Smem<2>), ctx->stream>>>(s, T[0], tm_pin, T[3]);
+    if (mode == 2) DPP_CUDA(launch_pdl(k_cg_fused_apply<2, 2>, grid, block, sizeof(Smem<2>), ctx->stream, s, T[0], tm_pin, tm_rx));
+    else if (mode == 1) DPP_CUDA(launch_pdl(k_cg_fused_apply<2, 1>, grid, block, sizeof(Smem<2>), ctx->stream, s, T[0], tm_pin, T[3]));
+    else k_cg_fused_apply<2, 0><<<grid, block, sizeof(Smem<2>), ctx->stream>>>(s, T[0], tm_pin, T[3]);
   } else {
-    if (fused) DPP_CUDA(launch_pdl(k_cg_fused_apply<1, true>, grid, block, sizeof(Smem<1>), ctx->stream, s, T[0], tm_pin, T[3]));
-    else k_cg_fused_apply<1, false><<<grid, block, sizeof(Smem<1>), ctx->stream>>>(s, T[0], tm_pin, T[3]);
+    if (mode == 2) DPP_CUDA(launch_pdl(k_cg_fused_apply<1, 2>, grid, block, sizeof(Smem<1>), ctx->stream, s, T[0], tm_pin, tm_rx));
+    else if (mode == 1) DPP_CUDA(launch_pdl(k_cg_fused_apply<1, 1>, grid, block, sizeof(Smem<1>), ctx->stream, s, T[0], tm_pin, T[3]));
+    else k_cg_fused_apply<1, 0><<<grid, block, sizeof(Smem<1>), ctx->stream>>>(s, T[0], tm_pin, T[3]);
   }
   ctx->launches++;
   DPP_CUDA(cudaGetLastError());
@@ -1590,6 +1720,25 @@ int cg_fused_begin(dpp_context* ctx, int nf, const double* b) {
   return DPP_OK;
 }
 
+// The residual update recomputes w = A p (k_cg_fused_apply<NF, 2>) instead of reading a stored w when: degree 1, the
+// direction ring is in use, every field of the solve is in class-mask mode (Dirichlet set = domain boundary: the
+// computed nodes are exactly the free nodes) and the rank keeps interior planes to compute; slabs need the
+// peer-memory halo (the kernel pushes its boundary planes like k_cg_r_update).  DPP_NO_STENCIL_RUPD=1: stored w.
+static bool stencil_rupd(dpp_context* ctx, FusedState* F, int nf, const int* fld) {
+  const GridDesc& g = ctx->grid;
+  if (g.band != 1 || !F->defer || getenv("DPP_NO_STENCIL_RUPD") != nullptr) return false;
+  if (!(ctx->world == 1 || comm_ipc_halo_ready(ctx))) return false;
+  for (int f = 0; f < nf; ++f)
+    if (!(F->bc_full_gen[fld[f]] == ctx->bc_gen[fld[f]] && F->bc_full[fld[f]])) return false;
+  if (!(g.n[1] >= 3 && g.n[2] >= 3 && (g.n[0] >= 3 || g.n[0] == 1))) return false;
+  if (g.n[0] > 1) {
+    const long long uplane = (long long)g.n[1] * g.n[2];
+    int ib = (int)(ctx->owned_begin / uplane), ie = (int)(ctx->owned_end / uplane);
+    if (ie - ib < 3) return false;   // (the trimming rule of launch_apply then always removes the boundary planes)
+  }
+  return true;
+}
+
 // <r,z>, <z,z> of the initial residual + POST_CG_INIT
 int cg_fused_rz_init(dpp_context* ctx, int nf, const int* fld, int slot, const double* dtab) {
   FusedState* F = nullptr;
@@ -1605,9 +1754,13 @@ int cg_fused_rz_init(dpp_context* ctx, int nf, const int* fld, int slot, const d
 }
 
 // r -= alpha w (+ halo push), <r,z>, <z,z> + POST_CG_RZ
-int cg_fused_r_update(dpp_context* ctx, int nf, const int* fld, int slot, const double* dtab) {
+int cg_fused_r_update(dpp_context* ctx, int nf, const Coef& c, long long it, const int* fld, int slot, const double* dtab) {
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
+  if (stencil_rupd(ctx, F, nf, fld)) {   // iteration `it`: its direction p_it sits in ring buffer (it + 1) % 16
+    int nb = 0;
+    return launch_apply(ctx, F, nf, 2, c, F->tmr[nf - 1][(it + 1) % kXRing], nullptr, slot, dtab, false, &nb, true, true);
+  }
   RArgs a{};
   DPP_CHECK(make_rargs(ctx, F, nf, slot, dtab, &a, fld, POST_CG_RZ));
   dim3 grid(r_blocks(ctx, a), nf);
@@ -1637,7 +1790,8 @@ int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const 
     DPP_CHECK(launch_apply_q2(ctx, F, nf, c, F->pring[it % kXRing], pout_buf, slot, dtab, &nb));
   } else {
     const CUtensorMap& tm_pin = defer ? F->tmr[nf - 1][it % kXRing] : F->tm[nf - 1][1 + (int)(it & 1)];
-    DPP_CHECK(launch_apply(ctx, F, nf, true, c, tm_pin, pout_buf, slot, dtab, true, &nb, all_class_masked, defer));
+    DPP_CHECK(launch_apply(ctx, F, nf, 1, c, tm_pin, pout_buf, slot, dtab, true, &nb, all_class_masked, defer,
+                           stencil_rupd(ctx, F, nf, fld)));
   }
   if (!(ctx->world == 1 || comm_ipc_ready(ctx))) DPP_CHECK(reduce_partials(ctx, nb, 1, slot, POST_CG_PAP));
   if (all_class_masked) return DPP_OK;   // constrained rows never leave zero: no row fix-up needed
@@ -1746,7 +1900,7 @@ int cg_fused_halo_r(dpp_context* ctx, int nf, bool after_update, int slot) {
 int cg_fused_plain_apply(dpp_context* ctx, int nf, const Coef& c, bool want_dot, int* n_partial_blocks) {
   FusedState* F = nullptr;
   DPP_CHECK(fused_state(ctx, &F));
-  return launch_apply(ctx, F, nf, false, c, F->tm[nf - 1][1], nullptr, 0, ctx->d_dtab, want_dot, n_partial_blocks);
+  return launch_apply(ctx, F, nf, 0, c, F->tm[nf - 1][1], nullptr, 0, ctx->d_dtab, want_dot, n_partial_blocks);
 }
 
 double* cg_fused_buffer(dpp_context* ctx, int which) {

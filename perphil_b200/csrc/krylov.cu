@@ -244,7 +244,7 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
     auto batch = [&](long long kk0) -> int {
       for (int k = 0; k < every; ++k) {
         DPP_CHECK(cg_fused_apply(ctx, op.nf, coef, kk0 + k, fld, slot, dtab));
-        DPP_CHECK(cg_fused_r_update(ctx, op.nf, fld, slot, dtab));
+        DPP_CHECK(cg_fused_r_update(ctx, op.nf, coef, kk0 + k, fld, slot, dtab));
         DPP_CHECK(cg_fused_halo_r(ctx, op.nf, true, slot));
       }
       return DPP_OK;
@@ -252,7 +252,7 @@ int cg_run(dpp_context* ctx, const OpSpec& op, Pc& pc, const double* b, double* 
     // the p ping-pong repeats with period 2: batches of an even number of iterations are identical launch
     // sequences -> replayed as one CUDA graph after the first (directly launched) batch
     unsigned long long key = mix(mix(mix(ctx->state_gen, (unsigned long long)op.nf * 16 + op.row * 4 + pc.type),
-                                     (unsigned long long)every * 2 + cg_fused_variant(ctx)),
+                                     (unsigned long long)every * 4 + cg_fused_variant(ctx)),
                                  (unsigned long long)(uintptr_t)hist_device(ctx, slot));
     // Polling without a pipeline bubble: batch k+1 is enqueued BEFORE the host waits for the scalars of
     // batch k (copied into a pinned double buffer behind each batch).  Kernels launched past convergence
@@ -985,7 +985,7 @@ int krylov_time_cg_kernels(dpp_context* ctx, int warmup, int reps, double* apply
     for (int i = -warmup; i < reps; ++i) {
       if (i == 0) DPP_CUDA(cudaEventRecord(e0, ctx->stream));
       if (pass == 0) DPP_CHECK(cg_fused_apply(ctx, nf, coef, i + warmup, fld, slot, dtab));
-      else if (pass == 1) DPP_CHECK(cg_fused_r_update(ctx, nf, fld, slot, dtab));
+      else if (pass == 1) DPP_CHECK(cg_fused_r_update(ctx, nf, coef, i + warmup, fld, slot, dtab));
       else if (ctx->grid.band == 1) DPP_CHECK(cg_fused_plain_apply(ctx, 2, coef, true, &nb));
       else {   // degree 2: the stand-alone stencil kernel on the C-ABI layout (apply_structured_q2.cu)
         OpSpec op{};

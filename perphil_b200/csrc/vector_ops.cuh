@@ -50,12 +50,12 @@ int cg_xr_update(dpp_context* ctx, const VecLayout& L, double* x, double* r, con
 bool cg_fused_available(dpp_context* ctx, int nf, int operator_mode, int pc_type);
 // (the reductions + PETSc bookkeeping after each kernel are folded into the kernels, or run as
 //  reduce_partials + NCCL when neither single-GPU nor peer-memory)
-int cg_fused_variant(dpp_context* ctx);   // 1: deferred x update (direction ring), 0: x updated in the apply kernel
+int cg_fused_variant(dpp_context* ctx);   // 0: x updated in the apply kernel; 1: deferred x update (direction ring); 2: + residual update that recomputes A p
 int cg_fused_table(dpp_context* ctx, const Coef& c, int nf, int pc_type, const int* fld, double* d_tab);
 int cg_fused_begin(dpp_context* ctx, int nf, const double* b);
 int cg_fused_rz_init(dpp_context* ctx, int nf, const int* fld, int slot, const double* dtab);
 int cg_fused_apply(dpp_context* ctx, int nf, const Coef& c, long long it, const int* fld, int slot, const double* dtab);
-int cg_fused_r_update(dpp_context* ctx, int nf, const int* fld, int slot, const double* dtab);
+int cg_fused_r_update(dpp_context* ctx, int nf, const Coef& c, long long it, const int* fld, int slot, const double* dtab);
 int cg_fused_x_finalize(dpp_context* ctx, int nf, long long its, int slot, double* x);
 int cg_fused_halo_r(dpp_context* ctx, int nf, bool after_update, int slot);
 int cg_fused_plain_apply(dpp_context* ctx, int nf, const Coef& c, bool want_dot, int* n_partial_blocks);

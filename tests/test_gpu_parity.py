@@ -591,6 +591,9 @@ def test_deferred_x_update_is_bitwise_the_per_iteration_update(cells, preset, mo
     W, p, bcs, osys = make_problem(cells, 1)
     params = {**(pb.B200_CG_JACOBI_PARAMS if preset == "jacobi" else pb.B200_CG_PARAMS), "b200_history": 4096}
     monkeypatch.delenv("DPP_NO_DEFER_X", raising=False)
+    # (the residual update that recomputes A p sums <r,z> over tiles instead of ranges: same numbers to rounding,
+    # not the same bits -- it has its own test below; here both sides read the stored w)
+    monkeypatch.setenv("DPP_NO_STENCIL_RUPD", "1")
     s1, u1, i1 = _solve_vec(W, p, bcs, params)
     s1b, u1b, _ = _solve_vec(W, p, bcs, params)
     monkeypatch.setenv("DPP_NO_DEFER_X", "1")
@@ -605,6 +608,42 @@ def test_deferred_x_update_is_bitwise_the_per_iteration_update(cells, preset, mo
     monkeypatch.setenv("DPP_NO_DEFER_X", "1")
     s4, u4, _ = _solve_vec(W, p, bcs2, params)
     monkeypatch.delenv("DPP_NO_DEFER_X", raising=False)
+    assert s3.iteration_number == s4.iteration_number and np.array_equal(u3, u4)
+    s5, u5, _ = _solve_vec(W, p, bcs, params)
+    assert np.array_equal(u5, u1)
+    pb.release_handles()
+
+
+@pytest.mark.parametrize("cells", [(12, 12, 12), (33, 9, 40), (16, 16), (40, 40, 40), (5, 7, 9)])
+@pytest.mark.parametrize("preset", ["jacobi", "none"])
+def test_stencil_residual_update_equals_stored_w(cells, preset, monkeypatch):
+    """k_cg_fused_apply<NF, 2> (r <- r - alpha A p with A p recomputed from the stored direction: one vector pass less
+    per iteration) against k_cg_r_update reading the w the apply kernel stored: same iteration counts, histories to
+    rounding, solutions; repeated solves bitwise repeatable; a partial Dirichlet set (no class mask) keeps the
+    stored-w path and still works on the same handle."""
+    W, p, bcs, osys = make_problem(cells, 1)
+    params = {**(pb.B200_CG_JACOBI_PARAMS if preset == "jacobi" else pb.B200_CG_PARAMS), "b200_history": 4096}
+    monkeypatch.delenv("DPP_NO_STENCIL_RUPD", raising=False)
+    s1, u1, i1 = _solve_vec(W, p, bcs, params)
+    s1b, u1b, _ = _solve_vec(W, p, bcs, params)
+    monkeypatch.setenv("DPP_NO_STENCIL_RUPD", "1")
+    s2, u2, i2 = _solve_vec(W, p, bcs, params)
+    monkeypatch.delenv("DPP_NO_STENCIL_RUPD", raising=False)
+    assert np.array_equal(u1, u1b) and s1.iteration_number == s1b.iteration_number
+    if preset == "jacobi":
+        assert s1.iteration_number == s2.iteration_number
+        assert np.allclose(i1.history, i2.history, rtol=1e-9, atol=0)
+    else:
+        assert its_close(s1.iteration_number, s2.iteration_number)
+    assert rel_err(u1, u2) < 1e-8
+    ref = orc.solve_dpp_oracle(osys, "cg", preset)
+    assert rel_err(u1, ref.u) < 1e-7
+    if preset == "jacobi":
+        assert s1.iteration_number == ref.iteration_number
+    s3, u3, _ = _solve_vec(W, p, [bcs[0]], params)
+    monkeypatch.setenv("DPP_NO_STENCIL_RUPD", "1")
+    s4, u4, _ = _solve_vec(W, p, [bcs[0]], params)
+    monkeypatch.delenv("DPP_NO_STENCIL_RUPD", raising=False)
     assert s3.iteration_number == s4.iteration_number and np.array_equal(u3, u4)
     s5, u5, _ = _solve_vec(W, p, bcs, params)
     assert np.array_equal(u5, u1)
