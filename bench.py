@@ -26,7 +26,8 @@ import numpy as np
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/): filled in after each profiling pass, None until a capture of the current kernel exists.
 TRAFFIC_NCU = {"fused_apply": 1648143872, "r_update": 819625216,   # profiles/r01_cg_kernels_final2.md (256^3)
-               "fused_apply_deferred": 1100252880}                 # profiles/r02_cg_kernels.md (256^3)
+               "fused_apply_deferred": 1100252880,                 # profiles/r02_cg_kernels.md (256^3)
+               "fused_apply_no_w": 850131968}                      # profiles/r02_cg_kernels_b.md (256^3)
 
 
 def measured_peaks():
@@ -475,12 +476,26 @@ def main():
     # r, p_old in and p, A p out; x is brought up to date by the r-update kernel every 15th iteration from a ring of
     # 16 direction buffers ((15 + 2) / 15 passes per iteration instead of 2)
     deferred = fused and os.environ.get("DPP_NO_DEFER_X") is None and (world == 1 or (info.peer_memory & 1))
-    if fused and deferred:
+    # residual update that recomputes A p (k_cg_fused_apply<2, 2>; default for full-boundary Dirichlet sets wherever x
+    # is deferred and, on slabs, the residual halo goes through peer memory): the iteration kernel stores no w
+    stencil_rupd = (deferred and os.environ.get("DPP_NO_STENCIL_RUPD") is None
+                    and (world == 1 or (info.peer_memory & 2)))
+    traffic_key = None
+    if fused and stencil_rupd:
+        dom_name = "k_cg_fused_apply<2, 1> (deferred x, no w store): p update + matrix-free apply + <p,Ap>"
+        dom_bytes = (3 * 8 + 1) * ndof
+        dom_ms = fa_ms
+        iter_bytes = dom_bytes + 3 * 8 * ndof + (17 * 8 * ndof) // 15
+        bytes_model = ("25 B/DoF: r, p_old in; p out; 1 B/DoF Dirichlet rows (A p is recomputed by the residual update "
+                       "k_cg_fused_apply<2, 2>: p, r in; r out = 24 B/DoF; x: 17/15 passes per iteration there)")
+        traffic_key = "fused_apply_no_w"
+    elif fused and deferred:
         dom_name = "k_cg_fused_apply<2> (deferred x): p update + matrix-free apply + <p,Ap>"
         dom_bytes = (4 * 8 + 1) * ndof
         dom_ms = fa_ms
         iter_bytes = dom_bytes + 3 * 8 * ndof + (17 * 8 * ndof) // 15
         bytes_model = "33 B/DoF: r, p_old in; p, Ap out; 1 B/DoF Dirichlet rows (x: 17/15 passes per iteration in k_cg_r_update)"
+        traffic_key = "fused_apply_deferred"
     elif fused:
         # k_cg_fused_apply: reads r, p_old, x and writes p, A p, x (6 passes of 8 B per DoF) + the 1 B/DoF
         # Dirichlet information (row fix-up list); k_cg_r_update: reads r, A p, writes r (3 passes)
@@ -489,6 +504,7 @@ def main():
         dom_ms = fa_ms
         iter_bytes = dom_bytes + 3 * 8 * ndof
         bytes_model = "49 B/DoF: r, p_old, x in; p, Ap, x out; 1 B/DoF Dirichlet rows"
+        traffic_key = "fused_apply"
     else:
         dom_name = "k_apply (matrix-free apply, fused <p,Ap>)"
         dom_bytes, dom_ms = apply_bytes, apply_ms
@@ -507,7 +523,7 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"3D hex Q1 {N}^3 monolithic DPP, matrix-free Jacobi-CG rtol 1e-8, manufactured BCs "
                                f"(BASELINE configs[2]); {ndof} DoF; inputs 10x L2, no flush needed",
-                   "preset": "B200_CG_JACOBI_PARAMS", "iterations": its, "x_update": "deferred (ring of 16)" if deferred else "per iteration", "parallelism": f"slab x{world}" + (" peer-memory halo + mailbox allreduce" if h.info().peer_memory == 3 else (" NCCL" if world > 1 else "")),
+                   "preset": "B200_CG_JACOBI_PARAMS", "iterations": its, "x_update": "deferred (ring of 16)" if deferred else "per iteration", "residual_update": "recomputes A p (no w vector)" if (fused and stencil_rupd) else "reads the stored w", "parallelism": f"slab x{world}" + (" peer-memory halo + mailbox allreduce" if h.info().peer_memory == 3 else (" NCCL" if world > 1 else "")),
                    "kernel_family": "structured" if structured else "general"},
         "iterations": its, "residual_error": sol.residual_error, "wall_ms_per_step": wall_ms,
         "lifting_setup_ms": float(np.mean(setup_ms)), "krylov_us_per_iteration": (ms - float(np.mean(setup_ms))) / its * 1e3,
@@ -526,8 +542,7 @@ def main():
                      "frac": achieved / peak,
                      # ncu dram bytes of ONE launch: captured on one GPU at 256^3 only (profiles/); no capture
                      # exists for the per-rank slab kernels, so N > 1 and other sizes report null
-                     "traffic": TRAFFIC_NCU.get("fused_apply_deferred" if deferred else "fused_apply")
-                     if (fused and world == 1 and N == 256) else None,
+                     "traffic": TRAFFIC_NCU.get(traffic_key) if (fused and world == 1 and N == 256) else None,
                      "peak_kind": peak_kind, "bytes_model": bytes_model,
                      "algorithmic_bytes": dom_bytes // world, "algorithmic_bytes_scope": "per rank, per launch",
                      "ms_per_launch": dom_ms},
