@@ -28,7 +28,7 @@ for i, ln in enumerate(lines):
         base = op.split(".")[0]
         if base in PAT:
             counts[kern][base] += 1
-        if op.startswith("UTMALDG") and "k_cg_fused_apply<2, true>" in kern and len(ctx.setdefault(kern, [])) < 6:
+        if op.startswith("UTMALDG") and "k_cg_fused_apply<2, 1>" in kern and len(ctx.setdefault(kern, [])) < 6:
             ctx[kern].append(ln.strip())
 print(f"# SASS excerpt of {so}\n")
 print(f"cubin architectures: {', '.join(arch)}\n")
