@@ -13,6 +13,11 @@
 // (bitwise the x of KSPCG).  The apply kernel then moves r, p_old in and p, w out (4 passes), x costs
 // (15 + 2) / 15 = 1.13 passes per iteration instead of 2: 8.13 passes per iteration; the ring takes 16 x 575 MB
 // of the 180 GB of HBM at 256^3.
+// Residual update with the stencil in it (default for full-boundary Dirichlet sets; DPP_NO_STENCIL_RUPD=1 restores the
+// scheme above): w = A p is not stored.  k_cg_fused_apply<NF, 2> -- the same plane-streaming kernel in its third mode
+// -- reads the direction the iteration kernel stored (with halo) and the r tiles, recomputes w with the identical
+// arithmetic and forms r, z, <r,z>, <z,z> (+ halo push, + the x accumulation): 3 + 3 + 1.13 = 7.13 passes.
+// Degree 2 (second half of this file): k_cg_fused_apply_q2, cp.async plane ring on the same padded layout.
 // The reciprocal diagonal is never read from memory: on a uniform grid diag(A) takes one of 8 values
 // per field (node on the domain boundary of axis x/y/z or not), kept in a 16-entry table.
 //
