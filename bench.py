@@ -549,7 +549,14 @@ def main():
         "kernels": {"cg_fused_apply_ms": fa_ms, "cg_r_update_ms": fu_ms, "tma_matvec_ms": mv_ms, "plain_apply_ms": apply_ms,
                     "plain_apply_gbs": apply_bytes / (apply_ms * 1e-3) / 1e9 / world,
                     "plain_apply_frac": apply_bytes / (apply_ms * 1e-3) / 1e9 / world / peak,
-                    "plain_apply_bytes_model": "34 B/node structured" if structured else "58 B/node + 32 B/cell"},
+                    "plain_apply_bytes_model": "34 B/node structured" if structured else "58 B/node + 32 B/cell",
+                    # the residual-update mode of the same kernel (the other half of the iteration, 52 % of the kernel
+                    # time in profiles/r02_launches_b.md): 24 B/DoF per launch + the x accumulation (17 passes) that
+                    # one launch of the 20-launch timing loop of dpp_time_cg_kernels carries
+                    "cg_r_update_gbs": ((24 * ndof + (17 * 8 * ndof) // 20) / (fu_ms * 1e-3) / 1e9 / world
+                                        if (fused and stencil_rupd) else None),
+                    "cg_r_update_frac": ((24 * ndof + (17 * 8 * ndof) // 20) / (fu_ms * 1e-3) / 1e9 / world / peak
+                                         if (fused and stencil_rupd) else None)},
         "solve_roofline": {"achieved": solve_gbs, "peak": peak, "unit": "GB/s", "frac": solve_gbs / peak,
                            "bytes_per_iteration": iter_bytes},
     }
