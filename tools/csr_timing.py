@@ -4,7 +4,14 @@ sys.path.insert(0, '.')
 import numpy as np
 import perphil_b200 as pb
 from perphil_b200 import _lib as L
-from tests.util import configured_handle
+from perphil_b200.solver import configure_handle
+
+
+def configured_handle(W, prm, bcs):
+    """Handle of W with the parameters and Dirichlet data uploaded (package API only: no test / oracle imports)."""
+    h = pb.handle_for(W)
+    configure_handle(h, W, prm, bcs)
+    return h
 import ctypes as C
 for N in (64, 128):
     mesh = pb.UnitCubeMesh(N, N, N)

@@ -3,7 +3,14 @@ of the fused Jacobi-CG iteration (time_cg_kernels) and, with `solve`, 48 iterati
 import sys
 sys.path.insert(0, '.')
 import perphil_b200 as pb
-from tests.util import configured_handle
+from perphil_b200.solver import configure_handle
+
+
+def configured_handle(W, prm, bcs):
+    """Handle of W with the parameters and Dirichlet data uploaded (package API only: no test / oracle imports)."""
+    h = pb.handle_for(W)
+    configure_handle(h, W, prm, bcs)
+    return h
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 mesh = pb.UnitCubeMesh(N, N, N)
 _, V = pb.create_function_spaces(mesh, pressure_deg=2); W = V * V

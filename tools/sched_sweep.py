@@ -3,7 +3,12 @@ import os, sys, subprocess
 sys.path.insert(0, '.')
 if len(sys.argv) > 1:
     import perphil_b200 as pb
-    from tests.util import configured_handle
+    from perphil_b200.solver import configure_handle
+
+    def configured_handle(W, prm, bcs):
+        h = pb.handle_for(W)
+        configure_handle(h, W, prm, bcs)
+        return h
     nx = int(sys.argv[1])
     mesh = pb.UnitCubeMesh(nx, 256, 256)
     _, V = pb.create_function_spaces(mesh); W = V * V
